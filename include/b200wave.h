@@ -1,0 +1,188 @@
+/*
+ * b200wave.h -- C ABI of libb200wave.so: the B200 (sm_100a) 2-D wavelet filterbank engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of fbcotter/pytorch_wavelets:
+ * the per-level separable analysis / synthesis filter banks behind DWTForward / DWTInverse,
+ * DTCWTForward / DTCWTInverse and the ScatLayer magnitude epilogue.  The reference has no FFI
+ * of its own; its narrowest stable interface is the torch.autograd.Function layer, so there is
+ * exactly one entry point here per reference Function.forward (each cites the reference
+ * file:line it replaces).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add to bind them.
+ *
+ * Conventions
+ *   - All image tensors are fp32, device memory, NCHW; "planes" = N*C independent images.
+ *   - Filter taps are HOST pointers to fp32 arrays holding the taps exactly as the reference
+ *     stores them in its module buffers (analysis filters time-reversed, synthesis filters
+ *     as-is: reference dwt/lowlevel.py:916-920,970; dtcwt/lowlevel.py:58-67).  They are copied
+ *     into kernel parameters (constant bank) by value; no device filter memory is needed.
+ *   - The caller owns every buffer, including outputs; the library never allocates device
+ *     memory, keeps no reference after return, has no global mutable state and is re-entrant.
+ *   - Every call is asynchronous on the given CUDA stream (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and never synchronises the host.
+ *   - Return value: 0 on success, a negative B200W_E* code otherwise (b200w_strerror()).
+ *     Shape / mode validation mirrors the reference's Python exceptions; the Python shell
+ *     raises the same exception types before calling, so C errors are defensive.
+ *   - mode integers are the reference's mode_to_int() codes (dwt/lowlevel.py:274-290).
+ */
+#ifndef B200WAVE_H
+#define B200WAVE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200W_VERSION 100 /* 0.1.0 */
+
+/* reference dwt/lowlevel.py:274-290 */
+enum {
+  B200W_MODE_ZERO = 0,
+  B200W_MODE_SYMMETRIC = 1,
+  B200W_MODE_PERIODIZATION = 2,
+  B200W_MODE_CONSTANT = 3, /* rejected by the filter banks, as in the reference */
+  B200W_MODE_REFLECT = 4,
+  B200W_MODE_REPLICATE = 5, /* rejected, as in the reference */
+  B200W_MODE_PERIODIC = 6
+};
+
+enum {
+  B200W_OK = 0,
+  B200W_EMODE = -1,   /* unknown / unsupported padding mode  (reference: ValueError "Unkown pad type") */
+  B200W_ESIZE = -2,   /* bad tensor size (reference: ValueError rows/cols multiple of 2 or 4)          */
+  B200W_EARG = -3,    /* null pointer / inconsistent arguments                                        */
+  B200W_EFILTER = -4, /* unsupported filter length                                                   */
+  B200W_ECUDA = -5,   /* CUDA launch error (cudaGetLastError captured)                                */
+  B200W_ENOTIMPL = -6 /* reference raises NotImplementedError here                                   */
+};
+
+#define B200W_MAX_TAPS 40 /* longest supported filter (db20) */
+
+int b200w_version(void);
+const char* b200w_strerror(int code);
+/* last CUDA error string seen by this thread's most recent failing call ("" if none) */
+const char* b200w_last_cuda_error(void);
+
+/* pywt.dwt_coeff_len as used at reference dwt/lowlevel.py:153: ceil(n/2) for periodization,
+ * floor((n+flen-1)/2) otherwise.  Returns <0 on bad input. */
+int b200w_dwt_coeff_len(int n, int flen, int mode);
+/* length produced by one synthesis level from k coefficients (reference dwt/lowlevel.py:242-267):
+ * 2k for periodization else 2k - flen + 2. */
+int b200w_dwt_rec_len(int k, int flen, int mode);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  one 2-D DWT analysis level.           Replaces AFB2D.forward, reference dwt/lowlevel.py:336-347
+ *     (afb1d along W then along H, :91-172; boundary index generation mypad :28-88).
+ *   x      (planes, H, W), row pitch x_pitch elements, plane stride x_plane_stride elements
+ *   ll     (planes, Ho, Wo) with ll_pitch / ll_plane_stride (lets the caller keep padded internal levels)
+ *   highs  (planes, 3, Ho, Wo) contiguous: [lh, hl, hh]; lh = low along W, high along H
+ *   fw_*   taps applied along W (the module buffers named *_col -- reference quirk,
+ *          dwt/transform2d.py:70-71 vs lowlevel.py:336), length Lw;  fh_* along H, length Lh.
+ *   Ho = b200w_dwt_coeff_len(H, Lh, mode), Wo = b200w_dwt_coeff_len(W, Lw, mode).
+ * Also computes SFB2D.backward (dwt/lowlevel.py:683-694) when given the synthesis taps.
+ */
+int b200w_dwt_afb2d(const float* x, long long x_plane_stride, int x_pitch,
+                    float* ll, long long ll_plane_stride, int ll_pitch,
+                    float* highs,
+                    int planes, int H, int W,
+                    const float* fw_lo, const float* fw_hi, int Lw,
+                    const float* fh_lo, const float* fh_hi, int Lh,
+                    int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  one 2-D DWT synthesis level.          Replaces SFB2D.forward, reference dwt/lowlevel.py:671-680
+ *     (sfb1d along H for (ll,lh) and (hl,hh), then along W; :226-271).
+ *   ll     (planes, Hc, Wc) pitched;  highs (planes, 3, Hc, Wc) contiguous, or NULL = zeros
+ *          (reference dwt/transform2d.py:137-139)
+ *   y      (planes, Ho, Wo) pitched.  Ho/Wo may be smaller than the natural size
+ *          b200w_dwt_rec_len(Hc, Lh, mode) -- the crop of AFB2D.backward (lowlevel.py:359-364).
+ *   gh_* taps along H (first pass), gw_* along W.
+ */
+int b200w_dwt_sfb2d(const float* ll, long long ll_plane_stride, int ll_pitch,
+                    const float* highs,
+                    float* y, long long y_plane_stride, int y_pitch,
+                    int planes, int Hc, int Wc, int Ho, int Wo,
+                    const float* gh_lo, const float* gh_hi, int Lh,
+                    const float* gw_lo, const float* gw_hi, int Lw,
+                    int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DTCWT.  "highs" is the reference's 6-D complex band-pass tensor; because o_dim / ri_dim are
+ * configurable (dtcwt/transform_funcs.py:10-58) it is described by six ELEMENT strides
+ * hs[6] = {n, c, orientation, row, col, real/imag}.  Default layout (N,C,6,H/2,W/2,2) is the
+ * fast path.  Orientation order 15,45,75,105,135,165 degrees (transform_funcs.py:61-72).
+ *
+ * K3  level-1 forward.                     Replaces FWD_J1.forward, dtcwt/transform_funcs.py:346-358
+ *     (fwd_j1 :98-121 = rowfilter x2, colfilter x4 (dtcwt/lowlevel.py:70-94), q2c :243-260).
+ *   x   (N*C, H, W) pitched, H and W even;  ll (N*C, H, W) pitched
+ *   highs: band-pass output at (H/2, W/2) or NULL when skip_hps.
+ *   h0,h1: stored (reversed) level-1 filters, odd lengths L0, L1.
+ *   mode: B200W_MODE_SYMMETRIC -> symmetric extension, anything else -> zero padding
+ *         (dtcwt/lowlevel.py:75-79).
+ * Also INV_J1.backward (:434-449) when given g0o/g1o.
+ */
+int b200w_dtcwt_fwd_j1(const float* x, long long x_plane_stride, int x_pitch,
+                       float* ll, long long ll_plane_stride, int ll_pitch,
+                       float* highs, const long long hs[6],
+                       int N, int C, int H, int W,
+                       const float* h0, int L0, const float* h1, int L1,
+                       int mode, void* stream);
+
+/* K4  level>=2 forward.                    Replaces FWD_J2PLUS.forward, transform_funcs.py:380-392
+ *     (fwd_j2plus :226-249 = rowdfilt x2, coldfilt x4 (dtcwt/lowlevel.py:97-151), q2c).
+ *   x (N*C,H,W) with H%4==0 and W%4==0 (else B200W_ESIZE, reference ValueError lowlevel.py:102-104);
+ *   ll (N*C,H/2,W/2); highs at (H/4,W/4) or NULL when skip_hps.
+ *   h0a,h1a,h0b,h1b: stored (reversed) q-shift filters, common even length m.
+ *   Always symmetric extension (transform_funcs.py:381).
+ * Also INV_J2PLUS.backward (:471-488) with a<->b swapped by the caller.
+ */
+int b200w_dtcwt_fwd_j2plus(const float* x, long long x_plane_stride, int x_pitch,
+                           float* ll, long long ll_plane_stride, int ll_pitch,
+                           float* highs, const long long hs[6],
+                           int N, int C, int H, int W,
+                           const float* h0a, const float* h1a,
+                           const float* h0b, const float* h1b, int m,
+                           void* stream);
+
+/* K5  level-1 inverse.                     Replaces INV_J1.forward, transform_funcs.py:419-431
+ *     (inv_j1 :152-184 = c2q (dtcwt/lowlevel.py:263-295), colfilter x4, rowfilter x2).
+ *   ll (N*C,H,W) pitched or NULL (treated as zeros); highs at (H/2,W/2) or NULL (low-pass only
+ *   path, which the reference runs with symmetric extension regardless of mode, :159);
+ *   y (N*C,H,W).  g0,g1 stored level-1 synthesis filters (odd lengths).
+ * Also FWD_J1.backward (:361-374) when given h0o/h1o.
+ */
+int b200w_dtcwt_inv_j1(const float* ll, long long ll_plane_stride, int ll_pitch,
+                       const float* highs, const long long hs[6],
+                       float* y, long long y_plane_stride, int y_pitch,
+                       int N, int C, int H, int W,
+                       const float* g0, int L0, const float* g1, int L1,
+                       int mode, void* stream);
+
+/* K6  level>=2 inverse.                    Replaces INV_J2PLUS.forward, transform_funcs.py:455-468
+ *     (inv_j2plus :279-307 = c2q, colifilt x4, rowifilt x2 (dtcwt/lowlevel.py:154-239)).
+ *   ll (N*C,H,W) or NULL; highs at (H/2,W/2) or NULL; y (N*C,2H,2W).  H, W even.
+ *   g0a,g1a,g0b,g1b stored q-shift synthesis filters, common even length m.
+ * Also FWD_J2PLUS.backward (:395-413) with a<->b swapped by the caller.
+ */
+int b200w_dtcwt_inv_j2plus(const float* ll, long long ll_plane_stride, int ll_pitch,
+                           const float* highs, const long long hs[6],
+                           float* y, long long y_plane_stride, int y_pitch,
+                           int N, int C, int H, int W,
+                           const float* g0a, const float* g1a,
+                           const float* g0b, const float* g1b, int m,
+                           void* stream);
+
+/* K7  ScatLayer forward.                   Replaces ScatLayerj1_f.forward (combine_colour=False),
+ *     scatternet/lowlevel.py:76-111: level-1 DTCWT (o_dim=1) -> 2x2 mean of ll ->
+ *     sqrt(re^2+im^2+b^2)-b -> stacked (N,7,C,H/2,W/2).
+ *   x (N,C,H,W) contiguous, H and W even; z (N,7,C,H/2,W/2) contiguous.
+ *   dre_dr / dim_dr: optional (N,6,C,H/2,W/2) outputs re/r and im/r saved for the backward
+ *   pass (:96-99); pass NULL when no gradient is needed.
+ */
+int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr,
+                  int N, int C, int H, int W,
+                  const float* h0, int L0, const float* h1, int L1,
+                  int mode, float magbias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200WAVE_H */

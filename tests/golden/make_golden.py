@@ -1,0 +1,119 @@
+"""Generate the committed golden vectors from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; imports it through oracle/refshim.py with
+the pywt stand-in):
+
+    python tests/golden/make_golden.py
+
+Each fixture is an .npz with the seeded input, the reference module's stored filter buffers and
+the reference's outputs, for one entry point of the hot path.  The GPU box has no /root/reference;
+tests there (and the CPU tests of the oracle) read only these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import refshim  # noqa: E402
+
+ref = refshim.load()
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, {k: v.shape for k, v in out.items() if v.ndim})
+
+
+def bufs(m, names):
+    return {n: getattr(m, n).detach().numpy().ravel() for n in names}
+
+
+def dwt_case(name, shape, J, wave, mode, seed):
+    torch.manual_seed(seed)
+    x = torch.randn(*shape)
+    f = ref.DWTForward(J=J, wave=wave, mode=mode)
+    i = ref.DWTInverse(wave=wave, mode=mode)
+    yl, yh = f(x)
+    y = i((yl, yh))
+    yh_drop = list(yh)
+    if J > 1:
+        yh_drop[0] = None
+    y_drop = i((yl, yh_drop))
+    d = dict(x=x, yl=yl, y=y, y_drop0=y_drop, J=J, mode=mode, wave=wave)
+    for j, h in enumerate(yh):
+        d['yh%d' % j] = h
+    d.update(bufs(f, ['h0_col', 'h1_col', 'h0_row', 'h1_row']))
+    d.update(bufs(i, ['g0_col', 'g1_col', 'g0_row', 'g1_row']))
+    save(name, **d)
+
+
+def dtcwt_case(name, shape, J, biort, qshift, o_dim, ri_dim, mode, seed, skip_hps=False, scale=100.0):
+    torch.manual_seed(seed)
+    x = scale * torch.randn(*shape)
+    f = ref.DTCWTForward(biort=biort, qshift=qshift, J=J, o_dim=o_dim, ri_dim=ri_dim, mode=mode,
+                         skip_hps=skip_hps)
+    i = ref.DTCWTInverse(biort=biort, qshift=qshift, o_dim=o_dim, ri_dim=ri_dim, mode=mode)
+    yl, yh = f(x)
+    yh_in = [None if h.shape == torch.Size([]) else h for h in yh]
+    y = i((yl, yh_in))
+    d = dict(x=x, yl=yl, y=y, J=J, mode=mode, biort=biort, qshift=qshift, o_dim=o_dim, ri_dim=ri_dim,
+             skip=np.array([h is None for h in yh_in]))
+    for j, h in enumerate(yh_in):
+        if h is not None:
+            d['yh%d' % j] = h
+    d.update(bufs(f, ['h0o', 'h1o', 'h0a', 'h0b', 'h1a', 'h1b']))
+    d.update(bufs(i, ['g0o', 'g1o', 'g0a', 'g0b', 'g1a', 'g1b']))
+    save(name, **d)
+
+
+def scat_case(name, shape, biort, mode, seed, magbias=1e-2):
+    torch.manual_seed(seed)
+    x = torch.randn(*shape)
+    s = ref.ScatLayer(biort=biort, mode=mode, magbias=magbias)
+    z = s(x)
+    s2 = torch.nn.Sequential(ref.ScatLayer(biort=biort, mode=mode, magbias=magbias),
+                             ref.ScatLayer(biort=biort, mode=mode, magbias=magbias))
+    z2 = s2(x)
+    save(name, x=x, z=z, z2=z2, h0o=s.h0o.detach().numpy().ravel(), h1o=s.h1o.detach().numpy().ravel(),
+         mode=mode, biort=biort, magbias=magbias)
+
+
+if __name__ == '__main__':
+    # BASELINE.json config 1: DWTForward J=1 db4 zero on randn(4,3,64,64) -- the bit-check case
+    dwt_case('dwt_c1_db4_zero_J1', (4, 3, 64, 64), 1, 'db4', 'zero', 0)
+    k = 1
+    for mode in ['zero', 'symmetric', 'reflect', 'periodic', 'periodization']:
+        dwt_case('dwt_db4_%s_J3_64' % mode, (1, 2, 64, 64), 3, 'db4', mode, k); k += 1
+        dwt_case('dwt_db3_%s_J2_37x50' % mode, (2, 1, 37, 50), 2, 'db3', mode, k); k += 1
+    dwt_case('dwt_db1_symmetric_J3_33x64', (1, 2, 33, 64), 3, 'db1', 'symmetric', k); k += 1
+    dwt_case('dwt_db8_zero_J2_96', (1, 1, 96, 96), 2, 'db8', 'zero', k); k += 1
+    dwt_case('dwt_db2_symmetric_J2_127x126', (1, 1, 127, 126), 2, 'db2', 'symmetric', k); k += 1
+
+    dtcwt_case('dtcwt_a_a_J3_64', (1, 2, 64, 64), 3, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 20)
+    dtcwt_case('dtcwt_a_a_J3_64_zero', (1, 2, 64, 64), 3, 'near_sym_a', 'qshift_a', 2, -1, 'zero', 21)
+    dtcwt_case('dtcwt_a_a_J3_100', (1, 1, 100, 100), 3, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 22)
+    dtcwt_case('dtcwt_a_a_J4_99x100', (1, 1, 99, 100), 4, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 23)
+    dtcwt_case('dtcwt_a_a_J2_104x101', (1, 2, 104, 101), 2, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 24)
+    dtcwt_case('dtcwt_b_b_J3_72x56', (1, 1, 72, 56), 3, 'near_sym_b', 'qshift_b', 2, -1, 'symmetric', 25)
+    dtcwt_case('dtcwt_ant_c_J3_64', (1, 1, 64, 64), 3, 'antonini', 'qshift_c', 2, -1, 'symmetric', 26)
+    dtcwt_case('dtcwt_leg_d_J2_48', (1, 1, 48, 48), 2, 'legall', 'qshift_d', 2, -1, 'symmetric', 27)
+    dtcwt_case('dtcwt_a_06_J2_40', (1, 1, 40, 40), 2, 'near_sym_a', 'qshift_06', 2, -1, 'symmetric', 28)
+    for n, (o, r) in enumerate([(1, 2), (4, 5), (3, 1), (5, 2), (2, 3), (1, -1)]):
+        dtcwt_case('dtcwt_a_a_J2_24x28_o%d_r%d' % (o, r % 6), (1, 2, 24, 28), 2, 'near_sym_a', 'qshift_a', o, r,
+                   'symmetric', 30 + n)
+    dtcwt_case('dtcwt_a_a_J3_64_skip1', (1, 2, 64, 64), 3, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 40,
+               skip_hps=[True, False, False])
+    dtcwt_case('dtcwt_a_a_J3_64_skip2', (1, 2, 64, 64), 3, 'near_sym_a', 'qshift_a', 2, -1, 'symmetric', 41,
+               skip_hps=[False, True, False])
+
+    scat_case('scat_a_sym_32', (2, 3, 32, 32), 'near_sym_a', 'symmetric', 50)
+    scat_case('scat_a_zero_31x29', (1, 2, 31, 29), 'near_sym_a', 'zero', 51)
+    scat_case('scat_b_sym_32', (1, 1, 32, 32), 'near_sym_b', 'symmetric', 52)
