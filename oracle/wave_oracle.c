@@ -48,6 +48,11 @@ enum { ORC_EMODE = -1, ORC_ESIZE = -2, ORC_EARG = -3, ORC_EFILTER = -4, ORC_EINT
 
 #define SQRT2_D 1.4142135623730951
 
+/* 0 (default): plane passes use the row-vectorised forms; 1: the plain *_line forms.  Both compute
+ * identical values (tests/test_oracle_golden.py::test_line_and_row_forms_identical). */
+static int orc_use_line_forms = 0;
+void orc_set_line_forms(int on) { orc_use_line_forms = on; }
+
 /* modes accepted by afb1d / sfb1d (dwt/lowlevel.py:134,155,165,263-264); anything else is the
  * reference's ValueError("Unkown pad type"). */
 static int orc_mode_ok(int mode) {

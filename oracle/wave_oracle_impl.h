@@ -139,22 +139,253 @@ static void FN(ifilt_line)(const T* x, long xs, int N, T* y, long ys, const T* h
   }
 }
 
+/* ---- row-vectorised forms of the same arithmetic -------------------------------------------------
+ * The *_line functions above are the readable statement of each 1-D operator.  The plane passes
+ * below compute exactly the same values (same products, same fused multiply-adds, same order over
+ * the tap index) but walk memory row-wise so the compiler can vectorise across independent outputs:
+ *   - along W: extend one row into a scratch line once, then taps outer / outputs inner;
+ *   - along H: one output row at a time, taps outer / columns inner.
+ * This is what makes the oracle usable as the CPU baseline (bench.py) without flattering the GPU. */
+
+/* build e[i] = x[ext(i + start)] (or 0) for i in [0, n) */
+static void FN(extend_line)(const T* x, int N, T* e, long start, int n, int mode) {
+  for (int i = 0; i < n; ++i) {
+    long g = orc_ext_index(start + i, N, mode);
+    e[i] = (g < 0) ? (T)0 : x[g];
+  }
+}
+
+/* afb along W for all rows of a plane */
+static void FN(afb_rows)(const T* x, long xpitch, int H, int W, T* lo, T* hi, int Wo, const T* f0, const T* f1,
+                         int L, int mode, T* e) {
+  const int pl = (mode == ORC_MODE_PER) ? (L - 1 - L / 2) : (L - 2);
+  const int n = 2 * (Wo - 1) + L;
+  for (int r = 0; r < H; ++r) {
+    FN(extend_line)(x + (long)r * xpitch, W, e, -pl, n, mode);
+    T* l = lo + (long)r * Wo;
+    T* h = hi + (long)r * Wo;
+    for (int k = 0; k < Wo; ++k) { T v = e[2 * k]; l[k] = f0[0] * v; h[k] = f1[0] * v; }
+    for (int j = 1; j < L; ++j) {
+      const T c0 = f0[j], c1 = f1[j];
+      for (int k = 0; k < Wo; ++k) { T v = e[2 * k + j]; l[k] = FMA(c0, v, l[k]); h[k] = FMA(c1, v, h[k]); }
+    }
+  }
+}
+
+/* afb along H: in (H, Wc) pitch inpitch -> a (Ho, Wc) pitch ap, b (Ho, Wc) pitch bp */
+static void FN(afb_cols)(const T* in, long inpitch, int H, int Wc, T* a, long ap, T* b, long bp, int Ho,
+                         const T* f0, const T* f1, int L, int mode) {
+  const int pl = (mode == ORC_MODE_PER) ? (L - 1 - L / 2) : (L - 2);
+  for (int k = 0; k < Ho; ++k) {
+    T* ra = a + (long)k * ap;
+    T* rb = b + (long)k * bp;
+    for (int j = 0; j < L; ++j) {
+      long g = orc_ext_index(2L * k + j - pl, H, mode);
+      const T c0 = f0[j], c1 = f1[j];
+      if (g < 0) {
+        if (j == 0) for (int c = 0; c < Wc; ++c) { ra[c] = c0 * (T)0; rb[c] = c1 * (T)0; }
+        else for (int c = 0; c < Wc; ++c) { ra[c] = FMA(c0, (T)0, ra[c]); rb[c] = FMA(c1, (T)0, rb[c]); }
+      } else {
+        const T* src = in + g * inpitch;
+        if (j == 0) for (int c = 0; c < Wc; ++c) { ra[c] = c0 * src[c]; rb[c] = c1 * src[c]; }
+        else for (int c = 0; c < Wc; ++c) { ra[c] = FMA(c0, src[c], ra[c]); rb[c] = FMA(c1, src[c], rb[c]); }
+      }
+    }
+  }
+}
+
+/* undecimated filter (colfilter/rowfilter) on a plane, odd or even L; acc: y += result */
+static void FN(filt_plane_fast)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* h, int L,
+                                int symmetric, int along_w, int acc, T* e, T* t) {
+  const int m = L / 2;
+  const int mode = symmetric ? ORC_MODE_SYMMETRIC : ORC_MODE_ZERO;
+  if (along_w) {
+    const int Wo = W + 2 * m - L + 1;
+    for (int r = 0; r < H; ++r) {
+      FN(extend_line)(x + (long)r * xpitch, W, e, -m, Wo + L - 1, mode);
+      T* yr = y + (long)r * ypitch;
+      for (int n = 0; n < Wo; ++n) t[n] = h[0] * e[n];
+      for (int j = 1; j < L; ++j) {
+        const T c = h[j];
+        for (int n = 0; n < Wo; ++n) t[n] = FMA(c, e[n + j], t[n]);
+      }
+      if (acc) for (int n = 0; n < Wo; ++n) yr[n] = yr[n] + t[n];
+      else for (int n = 0; n < Wo; ++n) yr[n] = t[n];
+    }
+  } else {
+    const int Ho = H + 2 * m - L + 1;
+    for (int n = 0; n < Ho; ++n) {
+      T* yr = y + (long)n * ypitch;
+      for (int j = 0; j < L; ++j) {
+        long g = orc_ext_index((long)n + j - m, H, mode);
+        const T c = h[j];
+        if (g < 0) {
+          if (j == 0) for (int q = 0; q < W; ++q) t[q] = c * (T)0;
+          else for (int q = 0; q < W; ++q) t[q] = FMA(c, (T)0, t[q]);
+        } else {
+          const T* src = x + g * xpitch;
+          if (j == 0) for (int q = 0; q < W; ++q) t[q] = c * src[q];
+          else for (int q = 0; q < W; ++q) t[q] = FMA(c, src[q], t[q]);
+        }
+      }
+      if (acc) for (int q = 0; q < W; ++q) yr[q] = yr[q] + t[q];
+      else for (int q = 0; q < W; ++q) yr[q] = t[q];
+    }
+  }
+}
+
+/* coldfilt/rowdfilt on a plane */
+static void FN(dfilt_plane_fast)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* ha,
+                                 const T* hb, int m, int highpass, int along_w, T* e, T* ta, T* tb) {
+  if (along_w) {
+    const int Q = W / 4;
+    for (int r = 0; r < H; ++r) {
+      /* e[i] = x[sym(i + 2 - m)], i in [0, 4(Q-1) + 2(m-1) + 2) */
+      FN(extend_line)(x + (long)r * xpitch, W, e, 2 - m, 4 * (Q - 1) + 2 * m, ORC_MODE_SYMMETRIC);
+      T* yr = y + (long)r * ypitch;
+      for (int q = 0; q < Q; ++q) { ta[q] = ha[0] * e[4 * q]; tb[q] = hb[0] * e[4 * q + 1]; }
+      for (int j = 1; j < m; ++j) {
+        const T ca = ha[j], cb = hb[j];
+        for (int q = 0; q < Q; ++q) {
+          ta[q] = FMA(ca, e[4 * q + 2 * j], ta[q]);
+          tb[q] = FMA(cb, e[4 * q + 2 * j + 1], tb[q]);
+        }
+      }
+      if (highpass) for (int q = 0; q < Q; ++q) { yr[2 * q] = tb[q]; yr[2 * q + 1] = ta[q]; }
+      else for (int q = 0; q < Q; ++q) { yr[2 * q] = ta[q]; yr[2 * q + 1] = tb[q]; }
+    }
+  } else {
+    const int Q = H / 4;
+    for (int q = 0; q < Q; ++q) {
+      T* ya = y + (long)(highpass ? 2 * q + 1 : 2 * q) * ypitch;
+      T* yb = y + (long)(highpass ? 2 * q : 2 * q + 1) * ypitch;
+      for (int j = 0; j < m; ++j) {
+        const T* sa = x + orc_ext_index(4L * q + 2 * j + 2 - m, H, ORC_MODE_SYMMETRIC) * xpitch;
+        const T* sb = x + orc_ext_index(4L * q + 2 * j + 3 - m, H, ORC_MODE_SYMMETRIC) * xpitch;
+        const T ca = ha[j], cb = hb[j];
+        if (j == 0) for (int c = 0; c < W; ++c) { ya[c] = ca * sa[c]; yb[c] = cb * sb[c]; }
+        else for (int c = 0; c < W; ++c) { ya[c] = FMA(ca, sa[c], ya[c]); yb[c] = FMA(cb, sb[c], yb[c]); }
+      }
+    }
+  }
+}
+
+/* colifilt/rowifilt on a plane; acc: y += result */
+static void FN(ifilt_plane_fast)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* ha,
+                                 const T* hb, int m, int highpass, int along_w, int acc, T* e, T* t) {
+  const int m2 = m / 2;
+  int o[4], par[4];
+  if (m2 % 2 == 0) {
+    par[0] = 0; par[1] = 0; par[2] = 1; par[3] = 1;
+    if (highpass) { o[0] = 1; o[1] = 0; o[2] = 3; o[3] = 2; } else { o[0] = 0; o[1] = 1; o[2] = 2; o[3] = 3; }
+  } else {
+    par[0] = 1; par[1] = 1; par[2] = 0; par[3] = 0;
+    if (highpass) { o[0] = 2; o[1] = 1; o[2] = 2; o[3] = 1; } else { o[0] = 1; o[1] = 2; o[2] = 1; o[3] = 2; }
+  }
+  if (along_w) {
+    const int Tn = W / 2;
+    for (int r = 0; r < H; ++r) {
+      /* e[i] = x[sym(i - m2)], i in [0, 2(Tn-1+m2-1) + 3 + 1) */
+      FN(extend_line)(x + (long)r * xpitch, W, e, -m2, 2 * (Tn + m2) + 2, ORC_MODE_SYMMETRIC);
+      T* yr = y + (long)r * ypitch;
+      for (int s = 0; s < 4; ++s) {
+        const T* h = (s & 1) ? hb : ha;
+        for (int u = 0; u < Tn; ++u) t[u] = h[par[s]] * e[2 * u + o[s]];
+        for (int j = 1; j < m2; ++j) {
+          const T c = h[2 * j + par[s]];
+          for (int u = 0; u < Tn; ++u) t[u] = FMA(c, e[2 * (u + j) + o[s]], t[u]);
+        }
+        if (acc) for (int u = 0; u < Tn; ++u) yr[4 * u + s] = yr[4 * u + s] + t[u];
+        else for (int u = 0; u < Tn; ++u) yr[4 * u + s] = t[u];
+      }
+    }
+  } else {
+    const int Tn = H / 2;
+    for (int u = 0; u < Tn; ++u)
+      for (int s = 0; s < 4; ++s) {
+        const T* h = (s & 1) ? hb : ha;
+        T* yr = y + (4L * u + s) * ypitch;
+        for (int j = 0; j < m2; ++j) {
+          const T* src = x + orc_ext_index(2L * (u + j) + o[s] - m2, H, ORC_MODE_SYMMETRIC) * xpitch;
+          const T c = h[2 * j + par[s]];
+          if (j == 0) for (int q = 0; q < W; ++q) t[q] = c * src[q];
+          else for (int q = 0; q < W; ++q) t[q] = FMA(c, src[q], t[q]);
+        }
+        if (acc) for (int q = 0; q < W; ++q) yr[q] = yr[q] + t[q];
+        else for (int q = 0; q < W; ++q) yr[q] = t[q];
+      }
+  }
+}
+
+/* sfb along H, row-wise: lo/hi (K, Wc) (either may be null = zeros) -> y (Nout, Wc) */
+static void FN(sfb_cols)(const T* lo, long lop, const T* hi, long hip, int K, int Wc, T* y, long yp, int Nout,
+                         const T* g0, const T* g1, int L, int mode, T* ta, T* tb) {
+  const int off = (mode == ORC_MODE_PER) ? (L / 2 - 1) : (L - 2);
+  for (int n = 0; n < Nout; ++n) {
+    long s = (long)n + off;
+    long kmin = orc_floordiv(s - L + 2, 2), kmax = orc_floordiv(s, 2);
+    int first = 1;
+    for (long k = kmin; k <= kmax; ++k) {
+      long kk = k;
+      if (mode == ORC_MODE_PER) { kk = k % K; if (kk < 0) kk += K; }
+      else if (k < 0 || k >= K) continue;
+      const int t = (int)(s - 2 * k);
+      const T c0 = g0[t], c1 = g1[t];
+      const T* rl = lo ? lo + kk * lop : (const T*)0;
+      const T* rh = hi ? hi + kk * hip : (const T*)0;
+      if (first) {
+        for (int c = 0; c < Wc; ++c) { ta[c] = (rl ? rl[c] : (T)0) * c0; tb[c] = (rh ? rh[c] : (T)0) * c1; }
+        first = 0;
+      } else {
+        for (int c = 0; c < Wc; ++c) {
+          ta[c] = FMA(rl ? rl[c] : (T)0, c0, ta[c]);
+          tb[c] = FMA(rh ? rh[c] : (T)0, c1, tb[c]);
+        }
+      }
+    }
+    T* yr = y + (long)n * yp;
+    if (first) for (int c = 0; c < Wc; ++c) yr[c] = (T)0 + (T)0;
+    else for (int c = 0; c < Wc; ++c) yr[c] = ta[c] + tb[c];
+  }
+}
+
 /* ---- plane-level passes (apply a line op along rows or columns of a (H,W) plane) ------------ */
 
 static void FN(filt_plane)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* h, int L,
                            int symmetric, int along_w, int acc) {
-  if (along_w) for (int r = 0; r < H; ++r) FN(filt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, h, L, symmetric, acc);
-  else for (int c = 0; c < W; ++c) FN(filt_line)(x + c, xpitch, H, y + c, ypitch, h, L, symmetric, acc);
+  if (orc_use_line_forms) {
+    if (along_w) for (int r = 0; r < H; ++r) FN(filt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, h, L, symmetric, acc);
+    else for (int c = 0; c < W; ++c) FN(filt_line)(x + c, xpitch, H, y + c, ypitch, h, L, symmetric, acc);
+    return;
+  }
+  const size_t n = (size_t)(H > W ? H : W) + 2 * (size_t)L + 8;
+  T* e = (T*)malloc(sizeof(T) * 2 * n);
+  FN(filt_plane_fast)(x, H, W, xpitch, y, ypitch, h, L, symmetric, along_w, acc, e, e + n);
+  free(e);
 }
 static void FN(dfilt_plane)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* ha, const T* hb,
                             int m, int highpass, int along_w) {
-  if (along_w) for (int r = 0; r < H; ++r) FN(dfilt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, ha, hb, m, highpass);
-  else for (int c = 0; c < W; ++c) FN(dfilt_line)(x + c, xpitch, H, y + c, ypitch, ha, hb, m, highpass);
+  if (orc_use_line_forms) {
+    if (along_w) for (int r = 0; r < H; ++r) FN(dfilt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, ha, hb, m, highpass);
+    else for (int c = 0; c < W; ++c) FN(dfilt_line)(x + c, xpitch, H, y + c, ypitch, ha, hb, m, highpass);
+    return;
+  }
+  const size_t n = (size_t)(H > W ? H : W) + 2 * (size_t)m + 8;
+  T* e = (T*)malloc(sizeof(T) * 3 * n);
+  FN(dfilt_plane_fast)(x, H, W, xpitch, y, ypitch, ha, hb, m, highpass, along_w, e, e + n, e + 2 * n);
+  free(e);
 }
 static void FN(ifilt_plane)(const T* x, int H, int W, long xpitch, T* y, long ypitch, const T* ha, const T* hb,
                             int m, int highpass, int along_w, int acc) {
-  if (along_w) for (int r = 0; r < H; ++r) FN(ifilt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, ha, hb, m, highpass, acc);
-  else for (int c = 0; c < W; ++c) FN(ifilt_line)(x + c, xpitch, H, y + c, ypitch, ha, hb, m, highpass, acc);
+  if (orc_use_line_forms) {
+    if (along_w) for (int r = 0; r < H; ++r) FN(ifilt_line)(x + r * xpitch, 1, W, y + r * ypitch, 1, ha, hb, m, highpass, acc);
+    else for (int c = 0; c < W; ++c) FN(ifilt_line)(x + c, xpitch, H, y + c, ypitch, ha, hb, m, highpass, acc);
+    return;
+  }
+  const size_t n = (size_t)(H > W ? H : W) + 2 * (size_t)m + 8;
+  T* e = (T*)malloc(sizeof(T) * 2 * n);
+  FN(ifilt_plane_fast)(x, H, W, xpitch, y, ypitch, ha, hb, m, highpass, along_w, acc, e, e + n);
+  free(e);
 }
 
 /* ---- exported single-primitive entry points (unit tests vs the reference primitives) -------- */
@@ -206,13 +437,22 @@ int FN(orc_dwt_afb2d)(const T* x, long long xps, int xpitch, T* ll, long long ll
     if (!lo) { err = 1; continue; }
     T* hi = lo + (size_t)H * Wo;
     const T* xp = x + (long long)p * xps;
-    for (int r = 0; r < H; ++r)
-      FN(afb_line)(xp + (long)r * xpitch, 1, W, lo + (long)r * Wo, 1, hi + (long)r * Wo, 1, Wo, fw_lo, fw_hi, Lw, mode);
     T* llp = ll + (long long)p * llps;
     T* hp = highs + (long long)p * 3 * Ho * Wo;
-    for (int c = 0; c < Wo; ++c) {
-      FN(afb_line)(lo + c, Wo, H, llp + c, llpitch, hp + c, Wo, Ho, fh_lo, fh_hi, Lh, mode);                     /* ll, lh */
-      FN(afb_line)(hi + c, Wo, H, hp + (long)Ho * Wo + c, Wo, hp + 2L * Ho * Wo + c, Wo, Ho, fh_lo, fh_hi, Lh, mode); /* hl, hh */
+    if (orc_use_line_forms) {
+      for (int r = 0; r < H; ++r)
+        FN(afb_line)(xp + (long)r * xpitch, 1, W, lo + (long)r * Wo, 1, hi + (long)r * Wo, 1, Wo, fw_lo, fw_hi, Lw, mode);
+      for (int c = 0; c < Wo; ++c) {
+        FN(afb_line)(lo + c, Wo, H, llp + c, llpitch, hp + c, Wo, Ho, fh_lo, fh_hi, Lh, mode);                     /* ll, lh */
+        FN(afb_line)(hi + c, Wo, H, hp + (long)Ho * Wo + c, Wo, hp + 2L * Ho * Wo + c, Wo, Ho, fh_lo, fh_hi, Lh, mode); /* hl, hh */
+      }
+    } else {
+      T* e = (T*)malloc(sizeof(T) * ((size_t)W + 2 * (size_t)Lw + 8));
+      if (!e) { err = 1; free(lo); continue; }
+      FN(afb_rows)(xp, xpitch, H, W, lo, hi, Wo, fw_lo, fw_hi, Lw, mode, e);
+      FN(afb_cols)(lo, Wo, H, Wo, llp, llpitch, hp, Wo, Ho, fh_lo, fh_hi, Lh, mode);                       /* ll, lh */
+      FN(afb_cols)(hi, Wo, H, Wo, hp + (long)Ho * Wo, Wo, hp + 2L * Ho * Wo, Wo, Ho, fh_lo, fh_hi, Lh, mode); /* hl, hh */
+      free(e);
     }
     free(lo);
   }
@@ -234,10 +474,19 @@ int FN(orc_dwt_sfb2d)(const T* ll, long long llps, int llpitch, const T* highs, 
     T* hi = lo + (size_t)Hn * Wc;
     const T* llp = ll + (long long)p * llps;
     const T* hp = highs ? highs + (long long)p * 3 * Hc * Wc : (const T*)0;
-    for (int c = 0; c < Wc; ++c) {
-      FN(sfb_line)(llp + c, llpitch, hp ? hp + c : 0, Wc, Hc, lo + c, Wc, Hn, gh_lo, gh_hi, Lh, mode);
-      FN(sfb_line)(hp ? hp + (long)Hc * Wc + c : 0, Wc, hp ? hp + 2L * Hc * Wc + c : 0, Wc, Hc, hi + c, Wc, Hn,
-                   gh_lo, gh_hi, Lh, mode);
+    if (orc_use_line_forms) {
+      for (int c = 0; c < Wc; ++c) {
+        FN(sfb_line)(llp + c, llpitch, hp ? hp + c : 0, Wc, Hc, lo + c, Wc, Hn, gh_lo, gh_hi, Lh, mode);
+        FN(sfb_line)(hp ? hp + (long)Hc * Wc + c : 0, Wc, hp ? hp + 2L * Hc * Wc + c : 0, Wc, Hc, hi + c, Wc, Hn,
+                     gh_lo, gh_hi, Lh, mode);
+      }
+    } else {
+      T* t = (T*)malloc(sizeof(T) * 2 * (size_t)Wc);
+      if (!t) { err = 1; free(lo); continue; }
+      FN(sfb_cols)(llp, llpitch, hp, Wc, Hc, Wc, lo, Wc, Hn, gh_lo, gh_hi, Lh, mode, t, t + Wc);
+      FN(sfb_cols)(hp ? hp + (long)Hc * Wc : 0, Wc, hp ? hp + 2L * Hc * Wc : 0, Wc, Hc, Wc, hi, Wc, Hn, gh_lo, gh_hi,
+                   Lh, mode, t, t + Wc);
+      free(t);
     }
     T* yp = y + (long long)p * yps;
     for (int r = 0; r < Ho; ++r)

@@ -1,0 +1,156 @@
+"""ctypes binding of libb200wave.so (the C ABI declared in include/b200wave.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built, or a tensor is not a
+CUDA float32 tensor, the call raises.  (The CPU oracle under oracle/ is test infrastructure and
+is never imported from here.)
+"""
+import collections
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'libb200wave.so')
+_lib = None
+
+c_ll = ctypes.c_longlong
+c_vp = ctypes.c_void_p
+c_int = ctypes.c_int
+
+# every symbol include/b200wave.h declares (tests/test_abi.py checks the library exports them all)
+SYMBOLS = [
+    'b200w_version', 'b200w_strerror', 'b200w_last_cuda_error', 'b200w_dwt_coeff_len', 'b200w_dwt_rec_len',
+    'b200w_dwt_afb2d', 'b200w_dwt_sfb2d', 'b200w_dtcwt_fwd_j1', 'b200w_dtcwt_fwd_j2plus', 'b200w_dtcwt_inv_j1',
+    'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1',
+]
+
+
+class B200WaveError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libb200wave.so (once).  Raises loudly when it is missing -- no CPU / eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise B200WaveError(
+                'libb200wave.so is not built (%s). Build it with `python -m pytorch_wavelets_b200._build` '
+                '(needs nvcc; compiles for sm_100a). There is no CPU fallback.' % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        L.b200w_strerror.restype = ctypes.c_char_p
+        L.b200w_last_cuda_error.restype = ctypes.c_char_p
+        pf = ctypes.c_void_p  # host tap pointers
+        L.b200w_dwt_afb2d.argtypes = [c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_int, c_int, c_int,
+                                      pf, pf, c_int, pf, pf, c_int, c_int, c_vp]
+        L.b200w_dwt_sfb2d.argtypes = [c_vp, c_ll, c_int, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      pf, pf, c_int, pf, pf, c_int, c_int, c_vp]
+        hs = ctypes.POINTER(c_ll)
+        L.b200w_dtcwt_fwd_j1.argtypes = [c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, hs, c_int, c_int, c_int, c_int,
+                                         pf, c_int, pf, c_int, c_int, c_vp]
+        L.b200w_dtcwt_fwd_j2plus.argtypes = [c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, hs, c_int, c_int, c_int,
+                                             c_int, pf, pf, pf, pf, c_int, c_vp]
+        L.b200w_dtcwt_inv_j1.argtypes = [c_vp, c_ll, c_int, c_vp, hs, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int,
+                                         pf, c_int, pf, c_int, c_int, c_vp]
+        L.b200w_dtcwt_inv_j2plus.argtypes = [c_vp, c_ll, c_int, c_vp, hs, c_vp, c_ll, c_int, c_int, c_int, c_int,
+                                             c_int, pf, pf, pf, pf, c_int, c_vp]
+        L.b200w_scat_j1.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, pf, c_int, pf, c_int, c_int,
+                                    ctypes.c_float, c_vp]
+        for s in ('b200w_debug_force_generic',):
+            getattr(L, s).argtypes = [c_int]
+            getattr(L, s).restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    """Map a negative return code to the exception type the reference raises in the same situation."""
+    if rc == 0:
+        return
+    L = lib()
+    msg = L.b200w_strerror(rc).decode()
+    if rc == -1:
+        raise ValueError('Unkown pad type')  # (sic) reference dwt/lowlevel.py:88,170,269
+    if rc == -2:
+        raise ValueError('%s: %s' % (what, msg))
+    if rc == -6:
+        raise NotImplementedError(what)
+    if rc == -5:
+        raise B200WaveError('%s: CUDA error: %s' % (what, L.b200w_last_cuda_error().decode()))
+    raise B200WaveError('%s: %s (code %d)' % (what, msg, rc))
+
+
+# ---- filter taps: host copies of the module buffers ------------------------------------------------
+# Kernels take their taps as by-value parameters (constant bank), so the C ABI wants HOST arrays.
+# Module buffers live on the device after .cuda(); reading them back costs a sync, so the host copy
+# is cached per (storage pointer, version counter) -- an in-place update of a buffer invalidates it.
+_TAPS = collections.OrderedDict()
+_TAPS_MAX = 512
+
+
+class HostTaps(object):
+    __slots__ = ('arr', 'ptr', 'n')
+
+    def __init__(self, arr):
+        self.arr = np.ascontiguousarray(arr, dtype=np.float32).ravel()
+        self.ptr = self.arr.ctypes.data_as(ctypes.c_void_p)
+        self.n = int(self.arr.size)
+
+
+def host_taps(t):
+    if isinstance(t, HostTaps):
+        return t
+    if not isinstance(t, torch.Tensor):
+        return HostTaps(np.asarray(t, dtype=np.float64))
+    key = (t.data_ptr(), t._version, t.numel(), t.device.type, t.device.index, t.dtype)
+    hit = _TAPS.get(key)
+    if hit is not None:
+        _TAPS.move_to_end(key)
+        return hit
+    h = HostTaps(t.detach().to('cpu', torch.float64).numpy())
+    _TAPS[key] = h
+    if len(_TAPS) > _TAPS_MAX:
+        _TAPS.popitem(last=False)
+    return h
+
+
+# ---- tensors ------------------------------------------------------------------------------------------
+
+def require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise NotImplementedError(
+            '%s is on %s: the b200wave engine runs on CUDA (sm_100a) only and has no CPU fallback' % (name, t.device))
+    if t.dtype != torch.float32:
+        raise NotImplementedError('%s has dtype %s: the b200wave engine computes in float32 only' % (name, t.dtype))
+
+
+def planes_view(t):
+    """(tensor, plane_stride, pitch) for a 4-D (N,C,H,W) tensor whose (N,C) dims collapse to one plane
+    index and whose rows are unit-stride; copies to contiguous only when the layout does not allow it."""
+    N, C, H, W = t.shape
+    s = t.stride()
+    ok = (W == 1 or s[3] == 1) and s[2] >= W
+    if ok and N > 1 and C > 1:
+        ok = (s[0] == C * s[1])
+    if not ok or t.numel() == 0:
+        t = t.contiguous()
+        s = t.stride()
+    if C > 1:
+        ps = s[1]
+    elif N > 1:
+        ps = s[0]
+    else:
+        ps = H * s[2]
+    return t, int(ps), int(s[2])
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def hs_array(hs):
+    return (c_ll * 6)(*[int(v) for v in hs])

@@ -1,0 +1,73 @@
+"""``ScatLayerj1_f``: one first-order DTCWT scattering layer as a single fused kernel (level-1 DTCWT,
+2x2 mean of the low-pass, smoothed magnitude of the six orientations, channel stacking) -- drop-in for
+the reference Function of the same name (``pytorch_wavelets/scatternet/lowlevel.py:71-137``,
+``combine_colour=False`` path)."""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from pytorch_wavelets_b200 import _ffi
+from pytorch_wavelets_b200.dtcwt.transform_funcs import inv_j1
+from pytorch_wavelets_b200.dwt.lowlevel import int_to_mode, mode_to_int  # noqa: F401  (re-exported like the reference)
+
+
+def scat_j1(x, h0o, h1o, mode, bias, want_aux):
+    """z (N,7,C,H/2,W/2) [, re/r, im/r (N,6,C,H/2,W/2)] from x (N,C,H,W), H and W even."""
+    _ffi.require_cuda_f32(x, 'x')
+    L = _ffi.lib()
+    h0, h1 = _ffi.host_taps(h0o), _ffi.host_taps(h1o)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    z = x.new_empty((N, 7, C, H // 2, W // 2))
+    dre = dim = None
+    if want_aux:
+        dre = x.new_empty((N, 6, C, H // 2, W // 2))
+        dim = torch.empty_like(dre)
+    if N * C > 0:
+        with torch.cuda.device(x.device):
+            rc = L.b200w_scat_j1(x.data_ptr(), z.data_ptr(), None if dre is None else dre.data_ptr(),
+                                 None if dim is None else dim.data_ptr(), N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n,
+                                 mode, float(bias), _ffi.stream_of(x))
+        _ffi.check(rc, 'b200w_scat_j1')
+    return z, dre, dim
+
+
+class ScatLayerj1_f(Function):
+    """``apply(x, h0o, h1o, mode, bias, combine_colour)`` -> Z of shape (N, 7, C, H/2, W/2)."""
+
+    @staticmethod
+    def forward(ctx, x, h0o, h1o, mode, bias, combine_colour):
+        if combine_colour:
+            raise NotImplementedError('combine_colour=True is outside the accelerated hot path (SURVEY 8(f) rank 2)')
+        ctx.in_shape = x.shape
+        batch, ch, r, c = x.shape
+        assert r % 2 == c % 2 == 0
+        mode = int(mode)
+        int_to_mode(mode)
+        ctx.mode = mode
+        want = bool(x.requires_grad)
+        z, dre, dim = scat_j1(x, h0o, h1o, mode, bias, want)
+        if want:
+            ctx.save_for_backward(h0o, h1o, dre, dim)
+        else:
+            zz = x.new_zeros(1)
+            ctx.save_for_backward(h0o, h1o, zz, zz)
+        return z
+
+    @staticmethod
+    def backward(ctx, dZ):
+        dX = None
+        if ctx.needs_input_grad[0]:
+            h0o, h1o, drdx, drdy = ctx.saved_tensors
+            dYl, dr = dZ[:, 0], dZ[:, 1:]
+            ll = 1 / 4 * F.interpolate(dYl, scale_factor=2, mode='nearest')
+            # band-pass gradient as one tensor with real/imag outermost: dims (r, n, o, c, h, w)
+            highs = torch.stack((dr * drdx, dr * drdy), dim=0)
+            dX = _inv_j1_ri_first(ll, highs, h0o, h1o, ctx.mode)
+        return (dX,) + (None,) * 5
+
+
+def _inv_j1_ri_first(ll, highs, g0, g1, mode):
+    """inv_j1 for a band-pass tensor laid out (2, N, 6, C, h, w).  transform_funcs._layout(o5, ri) inserts
+    'o' into (n,c,h,w) at o5 then 'r' at ri: o5=1 -> (n,o,c,h,w); ri=0 -> (r,n,o,c,h,w)."""
+    return inv_j1(ll, highs, g0, g1, 1, 0, mode)

@@ -1,0 +1,399 @@
+"""GPU parity tests (-m gpu): the CUDA path through the public nn.Module API / C ABI against
+  (1) the committed golden vectors produced by the reference itself (tests/golden),
+  (2) the CPU oracle on seeded random inputs over the reference's case matrix (odd sizes, all modes,
+      o_dim/ri_dim, skip_hps, None highs),
+  (3) size-independent properties at larger sizes (perfect reconstruction, linearity, adjoint identity).
+fp32 tolerance: RTOL_F32 (1e-5 of max|ref|), stated in tests/util.py; the DWT analysis path is
+additionally required to be bit-identical to the oracle (same FMA order)."""
+import numpy as np
+import pytest
+import torch
+
+import pytorch_wavelets_b200 as pw
+from oracle import oracle as orc
+from pytorch_wavelets_b200 import _ffi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = util.RTOL_F32
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _n(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _native_library_is_loaded():
+    """The CUDA extension must be the thing that runs: it has to load, and there is no fallback."""
+    assert torch.cuda.is_available()
+    lib = _ffi.lib()
+    assert lib.b200w_version() >= 100
+    yield
+
+
+# ---------------------------------------------------------------- golden vectors (reference outputs)
+
+@pytest.mark.parametrize('name', util.fixtures('dwt_'))
+def test_dwt_golden(name):
+    g = util.load(name)
+    J, mode, wave = int(g['J']), str(g['mode']), str(g['wave'])
+    f = pw.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+    i = pw.DWTInverse(wave=wave, mode=mode).to(DEV)
+    x = _t(g['x'])
+    yl, yh = f(x)
+    assert yl.is_contiguous() and all(h.is_contiguous() for h in yh)
+    util.assert_close(_n(yl), g['yl'], TOL, 'yl')
+    for j in range(J):
+        util.assert_close(_n(yh[j]), g['yh%d' % j], TOL, 'yh%d' % j)
+    y = i((_t(g['yl']), [_t(g['yh%d' % j]) for j in range(J)]))
+    util.assert_close(_n(y), g['y'], TOL, 'inverse')
+    yh_drop = [_t(g['yh%d' % j]) for j in range(J)]
+    if J > 1:
+        yh_drop[0] = None
+    util.assert_close(_n(i((_t(g['yl']), yh_drop))), g['y_drop0'], TOL, 'inverse None')
+
+
+def test_config1_bit_check():
+    """BASELINE.json configs[0]: DWTForward J=1 db4 zero on randn(4,3,64,64): max abs err <= 2e-6 and
+    the bit-equal fraction vs the reference's own CPU output is reported (expected 1.0)."""
+    g = util.load('dwt_c1_db4_zero_J1')
+    yl, yh = pw.DWTForward(J=1, wave='db4', mode='zero').to(DEV)(_t(g['x']))
+    assert np.abs(_n(yl) - g['yl']).max() <= 2e-6
+    assert np.abs(_n(yh[0]) - g['yh0']).max() <= 2e-6
+    frac = min(util.bit_equal_fraction(_n(yl), g['yl']), util.bit_equal_fraction(_n(yh[0]), g['yh0']))
+    print('config-1 bit-equal fraction vs reference CPU output: %.6f' % frac)
+    assert frac > 0.999
+
+
+@pytest.mark.parametrize('name', util.fixtures('dtcwt_'))
+def test_dtcwt_golden(name):
+    g = util.load(name)
+    J, mode = int(g['J']), str(g['mode'])
+    o_dim, ri_dim = int(g['o_dim']), int(g['ri_dim'])
+    skip = [bool(s) for s in g['skip']]
+    kw = dict(biort=str(g['biort']), qshift=str(g['qshift']), o_dim=o_dim, ri_dim=ri_dim, mode=mode)
+    f = pw.DTCWTForward(J=J, skip_hps=skip, **kw).to(DEV)
+    i = pw.DTCWTInverse(**kw).to(DEV)
+    yl, yh = f(_t(g['x']))
+    util.assert_close(_n(yl), g['yl'], TOL, 'yl')
+    for j in range(J):
+        if skip[j]:
+            assert yh[j].shape == torch.Size([])
+        else:
+            assert tuple(yh[j].shape) == g['yh%d' % j].shape
+            util.assert_close(_n(yh[j]), g['yh%d' % j], TOL, 'yh%d' % j)
+    yh_in = [None if skip[j] else _t(g['yh%d' % j]) for j in range(J)]
+    util.assert_close(_n(i((_t(g['yl']), yh_in))), g['y'], TOL, 'inverse')
+
+
+@pytest.mark.parametrize('name', util.fixtures('scat_'))
+def test_scat_golden(name):
+    g = util.load(name)
+    kw = dict(biort=str(g['biort']), mode=str(g['mode']), magbias=float(g['magbias']))
+    s = pw.ScatLayer(**kw).to(DEV)
+    z = s(_t(g['x']))
+    util.assert_close(_n(z), g['z'], TOL, 'z')
+    s2 = torch.nn.Sequential(pw.ScatLayer(**kw), pw.ScatLayer(**kw)).to(DEV)
+    util.assert_close(_n(s2(_t(g['x']))), g['z2'], TOL, 'z2')
+
+
+# ---------------------------------------------------------------- oracle on seeded random inputs
+
+DWT_MODES = ['zero', 'symmetric', 'reflect', 'periodic', 'periodization']
+
+
+@pytest.mark.parametrize('mode', DWT_MODES)
+@pytest.mark.parametrize('wave,J,shape', [('db4', 3, (3, 5, 128, 128)), ('db1', 3, (2, 3, 127, 126)),
+                                          ('db3', 2, (2, 2, 100, 99)), ('db8', 2, (1, 3, 190, 256)),
+                                          ('db2', 4, (1, 1, 201, 77)), ('db12', 1, (1, 2, 97, 64))])
+def test_dwt_vs_oracle(mode, wave, J, shape):
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    f = pw.DWTForward(J=J, wave=wave, mode=mode)
+    i = pw.DWTInverse(wave=wave, mode=mode)
+    L = f.h0_col.numel()
+    if mode == 'reflect' and min(shape[2:]) // (2 ** (J - 1)) <= L:
+        pytest.skip('reflect pad would exceed the signal')
+    hf = [b.numpy() for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    gf = [b.numpy() for b in (i.g0_col, i.g1_col, i.g0_row, i.g1_row)]
+    oyl, oyh = orc.dwt_forward(x.numpy(), hf, J, mode)
+    f, i = f.to(DEV), i.to(DEV)
+    yl, yh = f(x.to(DEV))
+    # same FMA order as the oracle: bit-identical (== ignores the sign of zero)
+    assert np.array_equal(_n(yl), oyl), util.rel_err(_n(yl), oyl)
+    for j in range(J):
+        assert np.array_equal(_n(yh[j]), oyh[j]), util.rel_err(_n(yh[j]), oyh[j])
+    oy = orc.dwt_inverse(oyl, oyh, gf, mode)
+    y = i((yl, yh))
+    assert np.array_equal(_n(y), oy), util.rel_err(_n(y), oy)
+    # perfect reconstruction on the original extent
+    H, W = shape[2:]
+    assert np.abs(_n(y)[:, :, :H, :W] - x.numpy()).max() < 2e-5
+
+
+def test_dwt_distinct_row_col_filters_quirk():
+    """4-tuple wave: the *_col filters act along W and *_row along H."""
+    torch.manual_seed(2)
+    x = torch.randn(2, 2, 32, 48)
+    wa, wb = pw.wavelets.Wavelet('db4'), pw.wavelets.Wavelet('db2')
+    f = pw.DWTForward(J=1, wave=(wa.dec_lo, wa.dec_hi, wb.dec_lo, wb.dec_hi), mode='symmetric')
+    hf = [b.numpy() for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    oyl, oyh = orc.dwt_forward(x.numpy(), hf, 1, 'symmetric')
+    yl, yh = f.to(DEV)(x.to(DEV))
+    assert tuple(yl.shape) == (2, 2, 17, 27)
+    assert np.array_equal(_n(yl), oyl) and np.array_equal(_n(yh[0]), oyh[0])
+
+
+def test_noncontiguous_and_offset_inputs():
+    torch.manual_seed(3)
+    big = torch.randn(2, 3, 70, 90, device=DEV)
+    x = big[:, :, 3:67, 5:85]  # strided view, pitch 90
+    f = pw.DWTForward(J=2, wave='db3', mode='symmetric').to(DEV)
+    a = f(x)
+    b = f(x.contiguous())
+    assert torch.equal(a[0], b[0]) and all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+    xt = big.transpose(2, 3)  # rows not unit-stride -> copied internally
+    a = f(xt)
+    b = f(xt.contiguous())
+    assert torch.equal(a[0], b[0])
+
+
+LAYOUTS = [(2, -1), (1, 2), (4, 5), (3, 1), (5, 2), (2, 3)]
+
+
+@pytest.mark.parametrize('biort,qshift', [('near_sym_a', 'qshift_a'), ('near_sym_b', 'qshift_b'),
+                                          ('antonini', 'qshift_c'), ('legall', 'qshift_d'),
+                                          ('near_sym_a', 'qshift_06')])
+@pytest.mark.parametrize('shape', [(2, 3, 128, 128), (1, 2, 100, 100), (1, 2, 99, 100), (1, 1, 104, 101)])
+def test_dtcwt_vs_oracle(biort, qshift, shape):
+    torch.manual_seed(4)
+    J = 3
+    x = 100 * torch.randn(*shape)
+    f = pw.DTCWTForward(biort=biort, qshift=qshift, J=J)
+    i = pw.DTCWTInverse(biort=biort, qshift=qshift)
+    l1 = (f.h0o.numpy(), f.h1o.numpy())
+    qs = (f.h0a.numpy(), f.h0b.numpy(), f.h1a.numpy(), f.h1b.numpy())
+    oyl, oyh = orc.dtcwt_forward(x.numpy(), l1, qs, J)
+    f, i = f.to(DEV), i.to(DEV)
+    yl, yh = f(x.to(DEV))
+    util.assert_close(_n(yl), oyl, TOL, 'yl')
+    for j in range(J):
+        util.assert_close(_n(yh[j]), oyh[j], TOL, 'yh%d' % j)
+    gl1 = (_n(i.g0o), _n(i.g1o))
+    gqs = (_n(i.g0a), _n(i.g0b), _n(i.g1a), _n(i.g1b))
+    oy = orc.dtcwt_inverse(oyl, oyh, gl1, gqs)
+    y = i((yl, yh))
+    util.assert_close(_n(y), oy, TOL, 'inverse')
+    H, W = shape[2:]
+    assert np.abs(_n(y)[:, :, :H, :W] - x.numpy()).max() < 2e-5 * 100 * 5  # perfect reconstruction
+    # None band-passes
+    for drop in (0, 1):
+        yh2 = list(yh)
+        yh2[drop] = None
+        oyh2 = list(oyh)
+        oyh2[drop] = None
+        util.assert_close(_n(i((yl, yh2))), orc.dtcwt_inverse(oyl, oyh2, gl1, gqs), TOL, 'inverse None %d' % drop)
+
+
+@pytest.mark.parametrize('o_dim,ri_dim', LAYOUTS)
+@pytest.mark.parametrize('mode', ['symmetric', 'zero'])
+def test_dtcwt_layouts_and_modes(o_dim, ri_dim, mode):
+    torch.manual_seed(5)
+    x = 100 * torch.randn(2, 3, 72, 88)
+    f = pw.DTCWTForward(J=2, o_dim=o_dim, ri_dim=ri_dim, mode=mode)
+    i = pw.DTCWTInverse(o_dim=o_dim, ri_dim=ri_dim, mode=mode)
+    l1 = (f.h0o.numpy(), f.h1o.numpy())
+    qs = (f.h0a.numpy(), f.h0b.numpy(), f.h1a.numpy(), f.h1b.numpy())
+    oyl, oyh = orc.dtcwt_forward(x.numpy(), l1, qs, 2, o_dim=o_dim, ri_dim=ri_dim, mode=mode)
+    gl1 = (i.g0o.numpy(), i.g1o.numpy())
+    gqs = (i.g0a.numpy(), i.g0b.numpy(), i.g1a.numpy(), i.g1b.numpy())
+    f, i = f.to(DEV), i.to(DEV)
+    yl, yh = f(x.to(DEV))
+    util.assert_close(_n(yl), oyl, TOL)
+    for j in range(2):
+        assert tuple(yh[j].shape) == oyh[j].shape
+        util.assert_close(_n(yh[j]), oyh[j], TOL)
+    util.assert_close(_n(i((yl, yh))), orc.dtcwt_inverse(oyl, oyh, gl1, gqs, o_dim, ri_dim, mode), TOL)
+
+
+def test_dtcwt_skip_hps_include_scale_and_j0():
+    torch.manual_seed(6)
+    x = torch.randn(1, 2, 64, 64, device=DEV)
+    f = pw.DTCWTForward(J=3, skip_hps=[True, False, True], include_scale=[False, True, True]).to(DEV)
+    scales, yh = f(x)
+    assert isinstance(scales, list) and scales[0].shape == torch.Size([])
+    assert tuple(scales[1].shape) == (1, 2, 32, 32) and tuple(scales[2].shape) == (1, 2, 16, 16)
+    assert yh[0].shape == torch.Size([]) and yh[2].shape == torch.Size([])
+    assert tuple(yh[1].shape) == (1, 2, 6, 16, 16, 2)
+    full = pw.DTCWTForward(J=3).to(DEV)(x)
+    assert torch.equal(scales[2], full[0]) and torch.equal(yh[1], full[1][1])
+    y0 = pw.DTCWTForward(J=0).to(DEV)(x)
+    assert y0[0] is x and y0[1] is None
+
+
+def test_dtcwt_inverse_asserts_like_reference():
+    i = pw.DTCWTInverse().to(DEV)
+    yl = torch.zeros(1, 1, 8, 8, device=DEV)
+    with pytest.raises(AssertionError):
+        i((yl, [torch.zeros(1, 1, 6, 8, 8, 2, device=DEV), torch.zeros(1, 1, 5, 4, 4, 2, device=DEV)]))
+
+
+@pytest.mark.parametrize('biort', ['near_sym_a', 'near_sym_b', 'antonini'])
+@pytest.mark.parametrize('shape', [(4, 3, 64, 64), (2, 1, 31, 29), (1, 2, 30, 32)])
+@pytest.mark.parametrize('mode', ['symmetric', 'zero'])
+def test_scat_vs_oracle(biort, shape, mode):
+    torch.manual_seed(7)
+    x = torch.randn(*shape)
+    s = pw.ScatLayer(biort=biort, mode=mode)
+    oz = orc.scat_layer(x.numpy(), (s.h0o.data.numpy(), s.h1o.data.numpy()), mode, 1e-2)
+    z = s.to(DEV)(x.to(DEV))
+    util.assert_close(_n(z), oz, TOL)
+
+
+# ---------------------------------------------------------------- autograd (adjoint identities)
+
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+def _flat_dot(ya, yb):
+    return sum(_dot(p, q) for p, q in zip(ya, yb))
+
+
+@pytest.mark.parametrize('mode', DWT_MODES)
+def test_dwt_backward_is_adjoint(mode):
+    """<A x, y> == <x, A^T y> with A^T computed by autograd (the reference's adjoint tests,
+    tests/test_dwt.py:215-299, in dot-product form)."""
+    torch.manual_seed(8)
+    f = pw.DWTForward(J=2, wave='db3', mode=mode).to(DEV)
+    x = torch.randn(2, 2, 45, 64, device=DEV, requires_grad=True)
+    yl, yh = f(x)
+    outs = [yl] + yh
+    ws = [torch.randn_like(o) for o in outs]
+    loss = sum((o * w).sum() for o, w in zip(outs, ws))
+    loss.backward()
+    x2 = torch.randn_like(x)
+    with torch.no_grad():
+        yl2, yh2 = f(x2)
+    lhs = _flat_dot([yl2] + yh2, ws)
+    rhs = _dot(x2, x.grad)
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+    # inverse
+    i = pw.DWTInverse(wave='db3', mode=mode).to(DEV)
+    cl = yl.detach().clone().requires_grad_(True)
+    ch = [h.detach().clone().requires_grad_(True) for h in yh]
+    y = i((cl, ch))
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    dl = torch.randn_like(cl)
+    dh = [torch.randn_like(h) for h in ch]
+    with torch.no_grad():
+        y2 = i((dl, dh))
+    lhs = _dot(y2, w)
+    rhs = _dot(dl, cl.grad) + sum(_dot(a, b.grad) for a, b in zip(dh, ch))
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize('o_dim,ri_dim', [(2, -1), (1, 2)])
+def test_dtcwt_backward_is_adjoint(o_dim, ri_dim):
+    torch.manual_seed(9)
+    f = pw.DTCWTForward(J=3, o_dim=o_dim, ri_dim=ri_dim).to(DEV)
+    x = torch.randn(2, 2, 64, 96, device=DEV, requires_grad=True)
+    yl, yh = f(x)
+    outs = [yl] + yh
+    ws = [torch.randn_like(o) for o in outs]
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    x2 = torch.randn_like(x)
+    with torch.no_grad():
+        yl2, yh2 = f(x2)
+    lhs = _flat_dot([yl2] + yh2, ws)
+    rhs = _dot(x2, x.grad)
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+    i = pw.DTCWTInverse(o_dim=o_dim, ri_dim=ri_dim).to(DEV)
+    cl = yl.detach().clone().requires_grad_(True)
+    ch = [h.detach().clone().requires_grad_(True) for h in yh]
+    y = i((cl, ch))
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    dl = torch.randn_like(cl)
+    dh = [torch.randn_like(h) for h in ch]
+    with torch.no_grad():
+        y2 = i((dl, dh))
+    lhs = _dot(y2, w)
+    rhs = _dot(dl, cl.grad) + sum(_dot(a, b.grad) for a, b in zip(dh, ch))
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+def test_scat_backward_matches_finite_difference():
+    torch.manual_seed(10)
+    s = pw.ScatLayer().to(DEV)
+    x = torch.randn(1, 2, 16, 16, device=DEV, requires_grad=True)
+    z = s(x)
+    w = torch.randn_like(z)
+    (z * w).sum().backward()
+    d = torch.randn_like(x)
+    eps = 1e-2
+    with torch.no_grad():
+        fd = (((s(x + eps * d) - s(x - eps * d)) * w).sum() / (2 * eps)).item()
+    an = _dot(d, x.grad)
+    assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
+
+
+# ---------------------------------------------------------------- properties at larger sizes
+
+def test_dwt_linearity_and_pr_large():
+    torch.manual_seed(11)
+    f = pw.DWTForward(J=3, wave='db4', mode='symmetric').to(DEV)
+    i = pw.DWTInverse(wave='db4', mode='symmetric').to(DEV)
+    a = torch.randn(8, 32, 512, 512, device=DEV)
+    b = torch.randn(8, 32, 512, 512, device=DEV)
+    ya, yb, yab = f(a), f(b), f(2 * a - 3 * b)
+    assert tuple(ya[0].shape) == (8, 32, 70, 70)
+    assert [tuple(h.shape[-2:]) for h in ya[1]] == [(259, 259), (133, 133), (70, 70)]
+    assert (yab[0] - (2 * ya[0] - 3 * yb[0])).abs().max() < 1e-3
+    for p, q, r in zip(ya[1], yb[1], yab[1]):
+        assert (r - (2 * p - 3 * q)).abs().max() < 1e-4
+    assert (i(ya) - a).abs().max() < 2e-5
+    # level-by-level consistency: J=3 equals three J=1 applications
+    f1 = pw.DWTForward(J=1, wave='db4', mode='symmetric').to(DEV)
+    l1, h1 = f1(a)
+    l2, h2 = f1(l1)
+    l3, h3 = f1(l2)
+    assert torch.equal(l3, ya[0]) and torch.equal(h1[0], ya[1][0]) and torch.equal(h3[0], ya[1][2])
+
+
+def test_dtcwt_pr_and_energy_large():
+    torch.manual_seed(12)
+    f = pw.DTCWTForward(J=3).to(DEV)
+    i = pw.DTCWTInverse().to(DEV)
+    x = torch.randn(8, 3, 1024, 1024, device=DEV)
+    yl, yh = f(x)
+    assert tuple(yl.shape) == (8, 3, 256, 256)
+    assert [tuple(h.shape) for h in yh] == [(8, 3, 6, 512, 512, 2), (8, 3, 6, 256, 256, 2), (8, 3, 6, 128, 128, 2)]
+    assert (i((yl, yh)) - x).abs().max() < 3e-5
+    # near-tight frame: energy of the coefficients ~ energy of the input (Kingsbury's DTCWT)
+    e_in = float((x.double() ** 2).sum())
+    e_out = float((yl.double() ** 2).sum()) + sum(float((h.double() ** 2).sum()) for h in yh)
+    assert abs(e_out / e_in - 1.0) < 0.05
+
+
+def test_generic_and_auto_paths_agree():
+    """Whatever kernel the dispatcher picks (specialised streaming or generic tile), results are identical."""
+    torch.manual_seed(13)
+    lib = _ffi.lib()
+    x = torch.randn(3, 4, 200, 264, device=DEV)
+    f = pw.DWTForward(J=3, wave='db4', mode='symmetric').to(DEV)
+    d = pw.DTCWTForward(J=3).to(DEV)
+    try:
+        lib.b200w_debug_force_generic(1)
+        a, b = f(x), d(x)
+    finally:
+        lib.b200w_debug_force_generic(0)
+    a2, b2 = f(x), d(x)
+    assert torch.equal(a[0], a2[0]) and all(torch.equal(p, q) for p, q in zip(a[1], a2[1]))
+    assert torch.equal(b[0], b2[0]) and all(torch.equal(p, q) for p, q in zip(b[1], b2[1]))

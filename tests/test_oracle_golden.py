@@ -90,3 +90,39 @@ def test_bad_mode_raises():
         orc.dwt_afb2d(x, [1, 1], [1, -1], [1, 1], [1, -1], 'constant')
     with pytest.raises(ValueError):
         orc.dwt_afb2d(x, [1, 1], [1, -1], [1, 1], [1, -1], 'bogus')
+
+
+def test_line_and_row_forms_identical():
+    """The oracle's readable per-line operators and its row-vectorised plane passes are the same
+    arithmetic: outputs are bit-identical."""
+    from pytorch_wavelets_b200.dtcwt._tables import TABLES
+    rng = np.random.default_rng(0)
+    lib = orc.lib()
+    x = rng.standard_normal((2, 2, 44, 60)).astype(np.float32)
+    g = util.load('dwt_db4_symmetric_J3_64')
+    hf = [g[k] for k in ('h0_col', 'h1_col', 'h0_row', 'h1_row')]
+    gf = [g[k] for k in ('g0_col', 'g1_col', 'g0_row', 'g1_row')]
+    rev = lambda t, k: np.array(TABLES[t][k])[::-1].copy()  # noqa: E731
+    l1 = (rev('near_sym_b', 'h0o'), rev('near_sym_b', 'h1o'))
+    qs = tuple(rev('qshift_c', k) for k in ('h0a', 'h0b', 'h1a', 'h1b'))
+    gl1 = (rev('near_sym_b', 'g0o'), rev('near_sym_b', 'g1o'))
+    gqs = tuple(rev('qshift_c', k) for k in ('g0a', 'g0b', 'g1a', 'g1b'))
+
+    def run():
+        out = []
+        for mode in ('zero', 'symmetric', 'reflect', 'periodic', 'periodization'):
+            yl, yh = orc.dwt_forward(x, hf, 2, mode)
+            out += [yl] + yh + [orc.dwt_inverse(yl, yh, gf, mode)]
+        yl, yh = orc.dtcwt_forward(x, l1, qs, 3)
+        out += [yl] + yh + [orc.dtcwt_inverse(yl, yh, gl1, gqs)]
+        out.append(orc.scat_layer(x, l1))
+        return out
+
+    fast = run()
+    lib.orc_set_line_forms(1)
+    try:
+        slow = run()
+    finally:
+        lib.orc_set_line_forms(0)
+    for a, b in zip(fast, slow):
+        assert np.array_equal(a, b)
