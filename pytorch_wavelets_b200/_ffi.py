@@ -154,3 +154,60 @@ def stream_of(t):
 
 def hs_array(hs):
     return (c_ll * 6)(*[int(v) for v in hs])
+
+
+# ---- optional per-call timing (bench.py roofline): CUDA events around each C-ABI launch ----------------
+_RECORDER = None
+
+
+class CallRecorder(object):
+    """``with CallRecorder() as rec:`` brackets every kernel launch made through this module with CUDA
+    events on the launching stream and remembers the algorithmic bytes (input read once + outputs written
+    once) of that launch.  ``summary()`` synchronises and returns per-kernel averages."""
+
+    def __init__(self):
+        self.spans = []
+        self.count = 0
+
+    def __enter__(self):
+        global _RECORDER
+        _RECORDER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _RECORDER
+        _RECORDER = None
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, nbytes, e0, e1 in self.spans:
+            d = out.setdefault(tag, {'tag': tag, 'count': 0, 'total_ms': 0.0, 'alg_bytes': nbytes})
+            d['count'] += 1
+            d['total_ms'] += e0.elapsed_time(e1)
+        for d in out.values():
+            d['avg_ms'] = d['total_ms'] / d['count']
+        return out
+
+
+class span(object):
+    """Context manager used by the launch wrappers; free when no recorder is active."""
+    __slots__ = ('tag', 'nbytes', 'e0', 'rec')
+
+    def __init__(self, tag, nbytes):
+        self.tag, self.nbytes, self.rec = tag, nbytes, _RECORDER
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.rec.spans.append((self.tag() if callable(self.tag) else self.tag, self.nbytes, self.e0, e1))
+            self.rec.count += 1
+        return False

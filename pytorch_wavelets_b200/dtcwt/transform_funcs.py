@@ -103,7 +103,8 @@ def fwd_j1(x, h0, h1, skip_hps, o5, ri, mode):
         shape, hs = highs_shape_strides(N, C, H // 2, W // 2, o5, ri)
         highs = x.new_empty(shape)
     if N * C > 0:
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j1 %dx%d' % (H, W),
+                                                    4 * N * C * H * W * (2 if skip_hps else 5)):
             rc = L.b200w_dtcwt_fwd_j1(x.data_ptr(), xps, xpitch, ll.data_ptr(), H * W, W,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                       N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n, mode, _ffi.stream_of(x))
@@ -127,7 +128,8 @@ def fwd_j2plus(x, h0a, h1a, h0b, h1b, skip_hps, o5, ri):
         shape, hs = highs_shape_strides(N, C, H // 4, W // 4, o5, ri)
         highs = x.new_empty(shape)
     if N * C > 0:
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j2plus %dx%d' % (H, W),
+                                                    N * C * H * W * (5 if skip_hps else 8)):
             rc = L.b200w_dtcwt_fwd_j2plus(x.data_ptr(), xps, xpitch, ll.data_ptr(), (H // 2) * (W // 2), W // 2,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                           N, C, H, W, f[0].ptr, f[1].ptr, f[2].ptr, f[3].ptr, f[0].n,
@@ -182,7 +184,8 @@ def inv_j1(ll, highs, g0, g1, o5, ri, mode):
         ll, llps, llpitch = _ffi.planes_view(ll)
     y = ref.new_empty((N, C, H, W))
     if N * C > 0:
-        with torch.cuda.device(ref.device):
+        with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j1 %dx%d' % (H, W),
+                                                      4 * N * C * H * W * (1 + (ll is not None) + 3 * (highs is not None))):
             rc = L.b200w_dtcwt_inv_j1(None if ll is None else ll.data_ptr(), llps, llpitch,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                       y.data_ptr(), H * W, W, N, C, H, W, g0.ptr, g0.n, g1.ptr, g1.n, mode,
@@ -215,7 +218,8 @@ def inv_j2plus(ll, highs, g0a, g1a, g0b, g1b, o5, ri):
         ll, llps, llpitch = _ffi.planes_view(ll)
     y = ref.new_empty((N, C, 2 * H, 2 * W))
     if N * C > 0:
-        with torch.cuda.device(ref.device):
+        with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j2plus %dx%d' % (H, W),
+                                                      4 * N * C * H * W * (4 + (ll is not None) + 3 * (highs is not None))):
             rc = L.b200w_dtcwt_inv_j2plus(None if ll is None else ll.data_ptr(), llps, llpitch,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                           y.data_ptr(), 4 * H * W, 2 * W, N, C, H, W,
