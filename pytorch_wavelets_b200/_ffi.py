@@ -4,7 +4,6 @@ There is deliberately NO fallback: if the CUDA library has not been built, or a 
 CUDA float32 tensor, the call raises.  (The CPU oracle under oracle/ is test infrastructure and
 is never imported from here.)
 """
-import collections
 import ctypes
 import os
 
@@ -84,11 +83,9 @@ def check(rc, what):
 
 # ---- filter taps: host copies of the module buffers ------------------------------------------------
 # Kernels take their taps as by-value parameters (constant bank), so the C ABI wants HOST arrays.
-# Module buffers live on the device after .cuda(); reading them back costs a sync, so the host copy
-# is cached per (storage pointer, version counter) -- an in-place update of a buffer invalidates it.
-_TAPS = collections.OrderedDict()
-_TAPS_MAX = 512
-
+# Module buffers live on the device after .cuda(); reading them back costs a sync, so the host copy is
+# cached ON THE TENSOR OBJECT together with its version counter: an in-place update (load_state_dict,
+# .copy_()) invalidates it, and a new tensor that happens to reuse a freed address can never alias it.
 
 class HostTaps(object):
     __slots__ = ('arr', 'ptr', 'n')
@@ -104,15 +101,14 @@ def host_taps(t):
         return t
     if not isinstance(t, torch.Tensor):
         return HostTaps(np.asarray(t, dtype=np.float64))
-    key = (t.data_ptr(), t._version, t.numel(), t.device.type, t.device.index, t.dtype)
-    hit = _TAPS.get(key)
-    if hit is not None:
-        _TAPS.move_to_end(key)
-        return hit
+    cached = getattr(t, '_b200w_host_taps', None)
+    if cached is not None and cached[0] == t._version:
+        return cached[1]
     h = HostTaps(t.detach().to('cpu', torch.float64).numpy())
-    _TAPS[key] = h
-    if len(_TAPS) > _TAPS_MAX:
-        _TAPS.popitem(last=False)
+    try:
+        t._b200w_host_taps = (t._version, h)
+    except Exception:
+        pass
     return h
 
 

@@ -243,17 +243,17 @@ class FWD_J1(Function):
     def forward(ctx, x, h0, h1, skip_hps, o_dim, ri_dim, mode):
         mode = _mode_int(mode)
         ctx.mode = mode
-        ctx.save_for_backward(h0, h1)
+        ctx.taps = (_ffi.host_taps(h0), _ffi.host_taps(h1))
         ctx.dims = get_dimensions5(o_dim, ri_dim)
         o5, ri = ctx.dims[0], ctx.dims[1]
-        ll, highs = fwd_j1(x, h0, h1, bool(skip_hps), o5, ri, mode)
+        ll, highs = fwd_j1(x, ctx.taps[0], ctx.taps[1], bool(skip_hps), o5, ri, mode)
         if highs is None:
             highs = ll.new_zeros([])
         return ll, highs
 
     @staticmethod
     def backward(ctx, dl, dh):
-        h0, h1 = ctx.saved_tensors
+        h0, h1 = ctx.taps
         dx = None
         if ctx.needs_input_grad[0]:
             o5, ri = ctx.dims[0], ctx.dims[1]
@@ -267,17 +267,17 @@ class FWD_J2PLUS(Function):
 
     @staticmethod
     def forward(ctx, x, h0a, h1a, h0b, h1b, skip_hps, o_dim, ri_dim, mode):
-        ctx.save_for_backward(h0a, h1a, h0b, h1b)
+        ctx.taps = tuple(_ffi.host_taps(f) for f in (h0a, h1a, h0b, h1b))
         ctx.dims = get_dimensions5(o_dim, ri_dim)
         o5, ri = ctx.dims[0], ctx.dims[1]
-        ll, highs = fwd_j2plus(x, h0a, h1a, h0b, h1b, bool(skip_hps), o5, ri)
+        ll, highs = fwd_j2plus(x, *ctx.taps, bool(skip_hps), o5, ri)
         if highs is None:
             highs = ll.new_zeros([])
         return ll, highs
 
     @staticmethod
     def backward(ctx, dl, dh):
-        h0a, h1a, h0b, h1b = ctx.saved_tensors
+        h0a, h1a, h0b, h1b = ctx.taps
         dx = None
         if ctx.needs_input_grad[0]:
             o5, ri = ctx.dims[0], ctx.dims[1]
@@ -293,15 +293,15 @@ class INV_J1(Function):
     def forward(ctx, lows, highs, g0, g1, o_dim, ri_dim, mode):
         mode = _mode_int(mode)
         ctx.mode = mode
-        ctx.save_for_backward(g0, g1)
+        ctx.taps = (_ffi.host_taps(g0), _ffi.host_taps(g1))
         ctx.dims = get_dimensions5(o_dim, ri_dim)
         ctx.has = (not _is_empty(lows), not _is_empty(highs))
         o5, ri = ctx.dims[0], ctx.dims[1]
-        return inv_j1(lows, highs, g0, g1, o5, ri, mode)
+        return inv_j1(lows, highs, ctx.taps[0], ctx.taps[1], o5, ri, mode)
 
     @staticmethod
     def backward(ctx, dy):
-        g0, g1 = ctx.saved_tensors
+        g0, g1 = ctx.taps
         o5, ri = ctx.dims[0], ctx.dims[1]
         need_l = ctx.needs_input_grad[0] and ctx.has[0]
         need_h = ctx.needs_input_grad[1] and ctx.has[1]
@@ -319,15 +319,15 @@ class INV_J2PLUS(Function):
 
     @staticmethod
     def forward(ctx, lows, highs, g0a, g1a, g0b, g1b, o_dim, ri_dim, mode):
-        ctx.save_for_backward(g0a, g1a, g0b, g1b)
+        ctx.taps = tuple(_ffi.host_taps(f) for f in (g0a, g1a, g0b, g1b))
         ctx.dims = get_dimensions5(o_dim, ri_dim)
         ctx.has = (not _is_empty(lows), not _is_empty(highs))
         o5, ri = ctx.dims[0], ctx.dims[1]
-        return inv_j2plus(lows, highs, g0a, g1a, g0b, g1b, o5, ri)
+        return inv_j2plus(lows, highs, *ctx.taps, o5, ri)
 
     @staticmethod
     def backward(ctx, dy):
-        g0a, g1a, g0b, g1b = ctx.saved_tensors
+        g0a, g1a, g0b, g1b = ctx.taps
         o5, ri = ctx.dims[0], ctx.dims[1]
         need_l = ctx.needs_input_grad[0] and ctx.has[0]
         need_h = ctx.needs_input_grad[1] and ctx.has[1]

@@ -163,19 +163,19 @@ class AFB2D(Function):
 
     @staticmethod
     def forward(ctx, x, h0_row, h1_row, h0_col, h1_col, mode):
-        ctx.save_for_backward(h0_row, h1_row, h0_col, h1_col)
+        ctx.taps = tuple(_ffi.host_taps(f) for f in (h0_row, h1_row, h0_col, h1_col))
         ctx.shape = x.shape[-2:]
         mode = int(mode)
         int_to_mode(mode)
         ctx.mode = mode
-        low, highs = afb2d_level(x, h0_row, h1_row, h0_col, h1_col, mode)
+        low, highs = afb2d_level(x, *ctx.taps, mode)
         return low, highs
 
     @staticmethod
     def backward(ctx, low, highs):
         dx = None
         if ctx.needs_input_grad[0]:
-            h0_row, h1_row, h0_col, h1_col = ctx.saved_tensors
+            h0_row, h1_row, h0_col, h1_col = ctx.taps
             dx = sfb2d_level(low.contiguous(), highs, h0_col, h1_col, h0_row, h1_row, ctx.mode, out_hw=ctx.shape)
         return dx, None, None, None, None, None
 
@@ -193,14 +193,15 @@ class SFB2D(Function):
         int_to_mode(mode)
         ctx.mode = mode
         ctx.has_highs = highs is not None
-        ctx.save_for_backward(g0_row, g1_row, g0_col, g1_col)
+        ctx.taps = tuple(_ffi.host_taps(f) for f in (g0_row, g1_row, g0_col, g1_col))
+        g0_row, g1_row, g0_col, g1_col = ctx.taps
         return sfb2d_level(low, highs, g0_col, g1_col, g0_row, g1_row, mode)
 
     @staticmethod
     def backward(ctx, dy):
         dlow, dhigh = None, None
         if ctx.needs_input_grad[0] or (ctx.has_highs and ctx.needs_input_grad[1]):
-            g0_row, g1_row, g0_col, g1_col = ctx.saved_tensors
+            g0_row, g1_row, g0_col, g1_col = ctx.taps
             dlow, dhigh = afb2d_level(dy.contiguous(), g0_row, g1_row, g0_col, g1_col, ctx.mode)
             if not ctx.has_highs:
                 dhigh = None

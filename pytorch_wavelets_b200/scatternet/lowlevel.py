@@ -47,19 +47,18 @@ class ScatLayerj1_f(Function):
         int_to_mode(mode)
         ctx.mode = mode
         want = bool(x.requires_grad)
-        z, dre, dim = scat_j1(x, h0o, h1o, mode, bias, want)
+        ctx.taps = (_ffi.host_taps(h0o), _ffi.host_taps(h1o))
+        z, dre, dim = scat_j1(x, ctx.taps[0], ctx.taps[1], mode, bias, want)
         if want:
-            ctx.save_for_backward(h0o, h1o, dre, dim)
-        else:
-            zz = x.new_zeros(1)
-            ctx.save_for_backward(h0o, h1o, zz, zz)
+            ctx.save_for_backward(dre, dim)
         return z
 
     @staticmethod
     def backward(ctx, dZ):
         dX = None
         if ctx.needs_input_grad[0]:
-            h0o, h1o, drdx, drdy = ctx.saved_tensors
+            h0o, h1o = ctx.taps
+            drdx, drdy = ctx.saved_tensors
             dYl, dr = dZ[:, 0], dZ[:, 1:]
             ll = 1 / 4 * F.interpolate(dYl, scale_factor=2, mode='nearest')
             # band-pass gradient as one tensor with real/imag outermost: dims (r, n, o, c, h, w)
