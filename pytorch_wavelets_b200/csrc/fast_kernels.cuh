@@ -1,6 +1,18 @@
 // fast_kernels.cuh -- specialised streaming kernels for the headline configurations (sm_100a).
-// (stub: fast paths are added incrementally; every try_launch_* returns kNoFastPath when no
-// specialisation applies and the caller falls back to the generic tile kernels.)
+//
+// Design (shared by all kernels in this file): one WARP owns a vertical strip of the plane and
+// marches down it.  Input rows are staged into a small per-warp shared-memory ring with cp.async
+// (16-byte, L1-bypassing; boundary columns/rows are remapped or zero-filled element-wise), several
+// stages ahead of the compute so HBM latency is covered by bytes in flight rather than by occupancy.
+// The pass along W reads each lane's window from the ring with aligned 128-bit LDS (conflict-free:
+// consecutive lanes read consecutive 16-byte words); the pass along H never touches memory: the
+// last L row-filtered rows live in a register window that is shifted as the warp advances (the
+// stage loop is unrolled by the window period so the shift is pure register renaming).  Filter taps
+// are kernel parameters: every FFMA takes its coefficient from the constant bank.  Warps are fully
+// independent (only __syncwarp), so there are no CTA barriers anywhere.
+//
+// Accumulation order is identical to the generic tile kernels / the oracle (stored-tap order, FMA),
+// so the two paths produce bit-identical results (tests/test_gpu_parity.py::test_generic_and_auto_paths_agree).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -12,7 +24,222 @@ namespace fast {
 constexpr int kNoFastPath = 1;
 static int g_force_generic = 0;
 
-inline int try_launch_afb(const AfbParams&, cudaStream_t) { return kNoFastPath; }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// store two adjacent outputs of one lane; nv = how many of them are inside the row (0..2)
+__device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, bool stream) {
+  if (nv == 2 && ((reinterpret_cast<uintptr_t>(ptr) & 7) == 0)) {
+    if (stream) __stcs(reinterpret_cast<float2*>(ptr), make_float2(v0, v1));
+    else *reinterpret_cast<float2*>(ptr) = make_float2(v0, v1);
+  } else {
+    if (nv > 0) { if (stream) __stcs(ptr, v0); else ptr[0] = v0; }
+    if (nv > 1) { if (stream) __stcs(ptr + 1, v1); else ptr[1] = v1; }
+  }
+}
+
+// ================================================================================================
+// K1 fast: DWT analysis level, Lw == Lh == L (even), modes zero / symmetric / reflect / periodic.
+//   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
+//   stage = 2 input rows = 1 output row.
+// ================================================================================================
+template <int L>
+struct AfbCfg {
+  static constexpr int HLA = ((L - 2) + 3) / 4 * 4;  // left halo rounded up to 16 bytes
+  static constexpr int SW = HLA + 128;               // staged floats per row
+  static constexpr int OFF = HLA - (L - 2);          // lane window offset inside its aligned read
+  static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
+  static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
+  static constexpr int CPR = SW / 4;                 // 16-byte chunks per staged row
+  static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
+  static constexpr int WARPS = 4;
+  static constexpr int SMEM_BYTES = WARPS * NS * 2 * SW * 4;
+  static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
+  static constexpr int UNR = (L / 2 > 0) ? L / 2 : 1;
+};
+
+template <int L>
+__global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
+                                                    int CH, int vec_ok) {
+  using C = AfbCfg<L>;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long item = (long long)blockIdx.x * C::WARPS + warp;
+  if (item >= (long long)p.planes * n_strips * n_chunks) return;  // whole warp leaves; no CTA barriers below
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+
+  float* ring = smem + warp * (C::NS * 2 * C::SW);
+  const int k0 = strip * 64;
+  const int ky0 = chunk * CH;
+  const int ky1 = imin(ky0 + CH, p.Ho);
+  const int n_stage = (ky1 - ky0) + C::PRO;
+  const int c_a = 2 * k0 - C::HLA;
+  const int r_begin = 2 * ky0 - (L - 2);
+  const int nvalid = imin(64, p.Wo - k0);
+  const int need_cols = C::HLA + 2 * nvalid;  // staged columns that feed a valid output
+  const int H = p.H, W = p.W, mode = p.mode, xpitch = p.xpitch;
+  const float* xp = p.x + (long long)plane * p.xps;
+
+  auto issue = [&](int t) {
+    if (t < n_stage) {
+      float* dst = ring + (t & (C::NS - 1)) * (2 * C::SW);
+      const int gr0 = ext_index(r_begin + 2 * t, H, mode);
+      const int gr1 = ext_index(r_begin + 2 * t + 1, H, mode);
+      for (int ch = lane; ch < 2 * C::CPR; ch += 32) {
+        const int rr = (ch >= C::CPR) ? 1 : 0;
+        const int cc = ch - rr * C::CPR;
+        if (4 * cc >= need_cols) continue;
+        const int gr = rr ? gr1 : gr0;
+        float* d = dst + rr * C::SW + 4 * cc;
+        const int gc = c_a + 4 * cc;
+        if (gr < 0) {
+          *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const float* src = xp + (long long)gr * xpitch;
+          if (vec_ok && gc >= 0 && gc + 3 < W) {
+            cp_async16(d, src + gc);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int g = ext_index(gc + e, W, mode);
+              if (g < 0) d[e] = 0.f;
+              else cp_async4(d + e, src + g);
+            }
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int t = 0; t < C::NS - 1; ++t) issue(t);
+
+  float wl[L][2], wh[L][2];
+#pragma unroll
+  for (int j = 0; j < L; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+
+  const long long band = (long long)p.Ho * p.Wo;
+  float* ll_base = p.ll + (long long)plane * p.llps + k0 + 2 * lane;
+  float* hi_base = p.highs + (long long)plane * 3 * band + k0 + 2 * lane;
+  const int nv = imax(0, imin(2, p.Wo - (k0 + 2 * lane)));
+
+#pragma unroll C::UNR
+  for (int t = 0; t < n_stage; ++t) {
+    cp_async_wait<C::NS - 2>();
+    __syncwarp();
+    issue(t + C::NS - 1);
+
+    const float* s0 = ring + (t & (C::NS - 1)) * (2 * C::SW) + 4 * lane;
+    float xa[4 * C::NV], xb[4 * C::NV];
+#pragma unroll
+    for (int q = 0; q < C::NV; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(s0 + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(s0 + C::SW + 4 * q);
+      xa[4 * q] = a.x; xa[4 * q + 1] = a.y; xa[4 * q + 2] = a.z; xa[4 * q + 3] = a.w;
+      xb[4 * q] = b.x; xb[4 * q + 1] = b.y; xb[4 * q + 2] = b.z; xb[4 * q + 3] = b.w;
+    }
+    // shift the window by two rows, then append the two new row-filtered rows
+#pragma unroll
+    for (int j = 0; j + 2 < L; ++j) {
+      wl[j][0] = wl[j + 2][0]; wl[j][1] = wl[j + 2][1];
+      wh[j][0] = wh[j + 2][0]; wh[j][1] = wh[j + 2][1];
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float la = 0.f, ha = 0.f, lb = 0.f, hb = 0.f;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const float f0 = p.fw_lo.t[j], f1 = p.fw_hi.t[j];
+        la = fmaf(f0, xa[C::OFF + 2 * o + j], la);
+        ha = fmaf(f1, xa[C::OFF + 2 * o + j], ha);
+        lb = fmaf(f0, xb[C::OFF + 2 * o + j], lb);
+        hb = fmaf(f1, xb[C::OFF + 2 * o + j], hb);
+      }
+      wl[L - 2][o] = la; wh[L - 2][o] = ha;
+      wl[L - 1][o] = lb; wh[L - 1][o] = hb;
+    }
+    if (t >= C::PRO) {
+      const int ky = ky0 + t - C::PRO;
+      float all[2], alh[2], ahl[2], ahh[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          const float f0 = p.fh_lo.t[j], f1 = p.fh_hi.t[j];
+          a0 = fmaf(f0, wl[j][o], a0);
+          a1 = fmaf(f1, wl[j][o], a1);
+          a2 = fmaf(f0, wh[j][o], a2);
+          a3 = fmaf(f1, wh[j][o], a3);
+        }
+        all[o] = a0; alh[o] = a1; ahl[o] = a2; ahh[o] = a3;
+      }
+      store2(ll_base + (long long)ky * p.llpitch, all[0], all[1], nv, false);
+      float* hr = hi_base + (long long)ky * p.Wo;
+      store2(hr, alh[0], alh[1], nv, true);
+      store2(hr + band, ahl[0], ahl[1], nv, true);
+      store2(hr + 2 * band, ahh[0], ahh[1], nv, true);
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int L>
+inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
+  using C = AfbCfg<L>;
+  const int n_strips = (p.Wo + 63) / 64;
+  // enough independent warps to fill the machine several times over; otherwise split the rows
+  const long long want = 148LL * 20 * 3;
+  const long long base = (long long)p.planes * n_strips;
+  int n_chunks = 1;
+  if (base < want) {
+    n_chunks = (int)((want + base - 1) / (base > 0 ? base : 1));
+    const int max_chunks = (p.Ho + 15) / 16;
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    if (n_chunks < 1) n_chunks = 1;
+  }
+  const int CH = (p.Ho + n_chunks - 1) / n_chunks;
+  n_chunks = (p.Ho + CH - 1) / CH;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && (p.xpitch % 4 == 0) && (p.xps % 4 == 0);
+  const long long items = base * n_chunks;
+  const long long blocks = (items + C::WARPS - 1) / C::WARPS;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return kNoFastPath;
+  afb2d_stream<L><<<(unsigned)blocks, 32 * C::WARPS, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, vec_ok);
+  return 0;
+}
+
+inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
+  if (g_force_generic) return kNoFastPath;
+  if (p.Lw != p.Lh || p.mode == B200W_MODE_PERIODIZATION) return kNoFastPath;
+  if (p.planes == 0) return 0;
+  switch (p.Lw) {
+    case 2: return launch_afb_stream<2>(p, stream);
+    case 4: return launch_afb_stream<4>(p, stream);
+    case 6: return launch_afb_stream<6>(p, stream);
+    case 8: return launch_afb_stream<8>(p, stream);
+    case 10: return launch_afb_stream<10>(p, stream);
+    case 12: return launch_afb_stream<12>(p, stream);
+    case 16: return launch_afb_stream<16>(p, stream);
+    default: return kNoFastPath;
+  }
+}
+
 inline int try_launch_fwd_j1(const DtParams&, cudaStream_t) { return kNoFastPath; }
 inline int try_launch_fwd_j2plus(const DtParams&, cudaStream_t) { return kNoFastPath; }
 

@@ -91,9 +91,11 @@ def prep_filt_sfb2d(g0_col, g1_col, g0_row=None, g1_row=None, device=None):
 
 # ---- raw kernel calls -----------------------------------------------------------------------------------
 
-def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, ll_out=None):
+def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     """One analysis level on the GPU.  ``fw_*`` filter along W, ``fh_*`` along H (stored/reversed taps).
-    Returns (ll (N,C,Ho,Wo), highs (N,C,3,Ho,Wo)), both contiguous."""
+    Returns (ll (N,C,Ho,Wo), highs (N,C,3,Ho,Wo)); highs is contiguous, ll is contiguous unless ``pad_ll``:
+    then its row pitch is rounded up to 16 bytes (an internal hand-off between levels, so the next level
+    can stage it with aligned 128-bit copies)."""
     _ffi.require_cuda_f32(x, 'x')
     _check_bank_mode(mode)
     if x.dim() != 4:
@@ -106,12 +108,15 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, ll_out=None):
     Ho = L.b200w_dwt_coeff_len(H, fh_lo.n, mode)
     Wo = L.b200w_dwt_coeff_len(W, fw_lo.n, mode)
     x, xps, xpitch = _ffi.planes_view(x)
-    ll = x.new_empty((N, C, Ho, Wo)) if ll_out is None else ll_out
+    Wp = (Wo + 3) // 4 * 4 if pad_ll else Wo
+    ll = x.new_empty((N, C, Ho, Wp))
+    if Wp != Wo:
+        ll = ll[..., :Wo]
     highs = x.new_empty((N, C, 3, Ho, Wo))
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dwt_afb2d %dx%d L%d' % (H, W, fw_lo.n),
                                                     4 * N * C * (H * W + 4 * Ho * Wo)):
-            rc = L.b200w_dwt_afb2d(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wo, Wo, highs.data_ptr(),
+            rc = L.b200w_dwt_afb2d(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wp, Wp, highs.data_ptr(),
                                    N * C, H, W, fw_lo.ptr, fw_hi.ptr, fw_lo.n, fh_lo.ptr, fh_hi.ptr, fh_lo.n,
                                    mode, _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dwt_afb2d')
@@ -162,13 +167,13 @@ class AFB2D(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, h0_row, h1_row, h0_col, h1_col, mode):
+    def forward(ctx, x, h0_row, h1_row, h0_col, h1_col, mode, pad_ll=False):
         ctx.taps = tuple(_ffi.host_taps(f) for f in (h0_row, h1_row, h0_col, h1_col))
         ctx.shape = x.shape[-2:]
         mode = int(mode)
         int_to_mode(mode)
         ctx.mode = mode
-        low, highs = afb2d_level(x, *ctx.taps, mode)
+        low, highs = afb2d_level(x, *ctx.taps, mode, pad_ll=bool(pad_ll))
         return low, highs
 
     @staticmethod
@@ -176,8 +181,8 @@ class AFB2D(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             h0_row, h1_row, h0_col, h1_col = ctx.taps
-            dx = sfb2d_level(low.contiguous(), highs, h0_col, h1_col, h0_row, h1_row, ctx.mode, out_hw=ctx.shape)
-        return dx, None, None, None, None, None
+            dx = sfb2d_level(low, highs, h0_col, h1_col, h0_row, h1_row, ctx.mode, out_hw=ctx.shape)
+        return dx, None, None, None, None, None, None
 
 
 class SFB2D(Function):

@@ -54,10 +54,13 @@ class DWTForward(nn.Module):
         yh = []
         ll = x
         mode = lowlevel.mode_to_int(self.mode)
-        for _ in range(self.J):
+        for j in range(self.J):
             # same argument order as reference transform2d.py:70-71: the *_col buffers land on the
             # Function's h*_row parameters and therefore filter along W; *_row buffers along H.
-            ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode)
+            # Intermediate low-passes are internal hand-offs: their row pitch is padded to 16 bytes so the
+            # next level stages them with aligned copies; the returned yl is contiguous.
+            ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode,
+                                            j < self.J - 1)
             yh.append(high)
         return ll, yh
 

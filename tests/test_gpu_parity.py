@@ -265,13 +265,14 @@ def _flat_dot(ya, yb):
     return sum(_dot(p, q) for p, q in zip(ya, yb))
 
 
-@pytest.mark.parametrize('mode', DWT_MODES)
-def test_dwt_backward_is_adjoint(mode):
-    """<A x, y> == <x, A^T y> with A^T computed by autograd (the reference's adjoint tests,
-    tests/test_dwt.py:215-299, in dot-product form)."""
+@pytest.mark.parametrize('mode,shape', [('zero', (2, 2, 45, 64)), ('periodization', (2, 2, 48, 64))])
+def test_dwt_backward_is_adjoint(mode, shape):
+    """<A x, y> == <x, A^T y> with A^T computed by autograd.  Holds where the reference's backward is the
+    true adjoint: zero padding, and periodization of even-sized inputs (for the other extensions the
+    reference's backward ignores the fold-back of the padding; see test_dwt_gradient_identities)."""
     torch.manual_seed(8)
     f = pw.DWTForward(J=2, wave='db3', mode=mode).to(DEV)
-    x = torch.randn(2, 2, 45, 64, device=DEV, requires_grad=True)
+    x = torch.randn(*shape, device=DEV, requires_grad=True)
     yl, yh = f(x)
     outs = [yl] + yh
     ws = [torch.randn_like(o) for o in outs]
@@ -283,7 +284,6 @@ def test_dwt_backward_is_adjoint(mode):
     lhs = _flat_dot([yl2] + yh2, ws)
     rhs = _dot(x2, x.grad)
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
-    # inverse
     i = pw.DWTInverse(wave='db3', mode=mode).to(DEV)
     cl = yl.detach().clone().requires_grad_(True)
     ch = [h.detach().clone().requires_grad_(True) for h in yh]
@@ -297,6 +297,48 @@ def test_dwt_backward_is_adjoint(mode):
     lhs = _dot(y2, w)
     rhs = _dot(dl, cl.grad) + sum(_dot(a, b.grad) for a, b in zip(dh, ch))
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize('wave,J,mode', [('db1', 1, 'zero'), ('db1', 3, 'zero'), ('db3', 1, 'symmetric'),
+                                         ('db3', 2, 'reflect'), ('db2', 3, 'periodization'), ('db4', 2, 'zero'),
+                                         ('db4', 2, 'periodic')])
+def test_dwt_gradient_identities(wave, J, mode):
+    """The reference's own gradient tests (tests/test_dwt.py:215-299): the gradient of the forward transform is
+    the inverse transform with the (time-reversed) analysis filters, and vice versa."""
+    torch.manual_seed(14)
+    w = pw.wavelets.Wavelet(wave)
+    fwd_filts = (w.dec_lo, w.dec_hi)
+    inv_filts = (w.dec_lo[::-1], w.dec_hi[::-1])
+    dwt = pw.DWTForward(J=J, wave=fwd_filts, mode=mode).to(DEV)
+    iwt = pw.DWTInverse(wave=inv_filts, mode=mode).to(DEV)
+    x = torch.randn(3, 2, 128, 128, device=DEV, requires_grad=True)
+    yl, yh = dwt(x)
+    ylg = torch.randn_like(yl)
+    yl.backward(ylg, retain_graph=True)
+    zeros = [torch.zeros_like(h) for h in yh]
+    ref = iwt((ylg, zeros))
+    assert (x.grad - ref).abs().max() < 1e-4
+    for j, y in enumerate(yh):
+        x.grad.zero_()
+        g = torch.randn_like(y)
+        y.backward(g, retain_graph=True)
+        hps = list(zeros)
+        hps[j] = g
+        ref = iwt((torch.zeros_like(yl), hps))
+        assert (x.grad - ref).abs().max() < 1e-4
+    # gradient of the inverse == forward with swapped filters
+    with torch.no_grad():
+        l, h = dwt(torch.zeros(3, 2, 128, 128, device=DEV))
+    cl = torch.randn_like(l).requires_grad_(True)
+    ch = [torch.randn_like(t).requires_grad_(True) for t in h]
+    y = iwt((cl, ch))
+    yg = torch.randn_like(y)
+    y.backward(yg)
+    with torch.no_grad():
+        dyl, dyh = dwt(yg)
+    assert (cl.grad - dyl).abs().max() < 1e-4
+    for a, b in zip(ch, dyh):
+        assert (a.grad - b).abs().max() < 1e-4
 
 
 @pytest.mark.parametrize('o_dim,ri_dim', [(2, -1), (1, 2)])
