@@ -38,6 +38,39 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Boundary handling stays out of line: the hot loop must fit the instruction cache (an inlined
+// ext_index drags three integer modulo sequences per call into every unrolled stage).
+// one 4-float chunk that touches the image border (or an unaligned source): element-wise remap
+__device__ __noinline__ void load_chunk_cold(float* d, const float* src_row, int gc, int W, int mode) {
+#pragma unroll 1
+  for (int e = 0; e < 4; ++e) {
+    const int g = ext_index(gc + e, W, mode);
+    if (g < 0) d[e] = 0.f;
+    else cp_async4(d + e, src_row + g);
+  }
+}
+// a whole stage of `rows` staged rows, fully general (rows outside the image, unaligned sources ...):
+// used for the few stages that touch the top/bottom border.
+__device__ __noinline__ void load_stage_cold(float* dst, int sw, int cpr, const float* plane, int r0, int rows,
+                                             int H, int W, int pitch, int mode, int c_a, int need_cols,
+                                             int vec_ok, int lane) {
+  for (int ch = lane; ch < rows * cpr; ch += 32) {
+    const int rr = ch / cpr;
+    const int cc = ch - rr * cpr;
+    if (4 * cc >= need_cols) continue;
+    const int gr = ext_index(r0 + rr, H, mode);
+    float* d = dst + rr * sw + 4 * cc;
+    const int gc = c_a + 4 * cc;
+    if (gr < 0) {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float* src = plane + (long long)gr * pitch;
+      if (vec_ok && gc >= 0 && gc + 3 < W) cp_async16(d, src + gc);
+      else load_chunk_cold(d, src, gc, W, mode);
+    }
+  }
+}
+
 // store two adjacent outputs of one lane; nv = how many of them are inside the row (0..2)
 __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, bool stream) {
   if (nv == 2 && ((reinterpret_cast<uintptr_t>(ptr) & 7) == 0)) {
@@ -62,12 +95,79 @@ struct AfbCfg {
   static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
   static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
   static constexpr int CPR = SW / 4;                 // 16-byte chunks per staged row
+  static constexpr int NCH = (2 * CPR + 31) / 32;    // chunks per lane per stage
   static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
   static constexpr int WARPS = 4;
   static constexpr int SMEM_BYTES = WARPS * NS * 2 * SW * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
-  static constexpr int UNR = (L / 2 > 0) ? L / 2 : 1;
+  static constexpr int UNR = L / 2;                  // window period: stage copies in the unrolled loop
 };
+
+// one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
+// the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
+// window period, so every window index is a compile-time constant: the window never moves.
+template <int L, int U>
+__device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
+                                          bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
+                                          int Wo, int nv) {
+  using C = AfbCfg<L>;
+  float xa[4 * C::NV], xb[4 * C::NV];
+#pragma unroll
+  for (int q = 0; q < C::NV; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(s0 + 4 * q);
+    const float4 b = *reinterpret_cast<const float4*>(s0 + C::SW + 4 * q);
+    xa[4 * q] = a.x; xa[4 * q + 1] = a.y; xa[4 * q + 2] = a.z; xa[4 * q + 3] = a.w;
+    xb[4 * q] = b.x; xb[4 * q + 1] = b.y; xb[4 * q + 2] = b.z; xb[4 * q + 3] = b.w;
+  }
+  constexpr int SA = (2 * U) % L, SB = (2 * U + 1) % L;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    float la = 0.f, ha = 0.f, lb = 0.f, hb = 0.f;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const float f0 = p.fw_lo.t[j], f1 = p.fw_hi.t[j];
+      la = fmaf(f0, xa[C::OFF + 2 * o + j], la);
+      ha = fmaf(f1, xa[C::OFF + 2 * o + j], ha);
+      lb = fmaf(f0, xb[C::OFF + 2 * o + j], lb);
+      hb = fmaf(f1, xb[C::OFF + 2 * o + j], hb);
+    }
+    wl[SA][o] = la; wh[SA][o] = ha;
+    wl[SB][o] = lb; wh[SB][o] = hb;
+  }
+  if (emit) {
+    float all[2], alh[2], ahl[2], ahh[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const float f0 = p.fh_lo.t[j], f1 = p.fh_hi.t[j];
+        constexpr int base = 2 * U + 2;
+        a0 = fmaf(f0, wl[(base + j) % L][o], a0);
+        a1 = fmaf(f1, wl[(base + j) % L][o], a1);
+        a2 = fmaf(f0, wh[(base + j) % L][o], a2);
+        a3 = fmaf(f1, wh[(base + j) % L][o], a3);
+      }
+      all[o] = a0; alh[o] = a1; ahl[o] = a2; ahh[o] = a3;
+    }
+    store2(ll_ptr, all[0], all[1], nv, false);
+    store2(hi_ptr, alh[0], alh[1], nv, true);
+    store2(hi_ptr + band, ahl[0], ahl[1], nv, true);
+    store2(hi_ptr + 2 * band, ahh[0], ahh[1], nv, true);
+    ll_ptr += llpitch;
+    hi_ptr += Wo;
+  }
+}
+
+template <int L, int U>
+__device__ __forceinline__ void afb_stage_dispatch(int uu, const AfbParams& p, const float* s0, float (&wl)[L][2],
+                                                   float (&wh)[L][2], bool emit, float*& ll_ptr, float*& hi_ptr,
+                                                   long long band, int llpitch, int Wo, int nv) {
+  if constexpr (U < AfbCfg<L>::UNR) {
+    if (uu == U) afb_stage<L, U>(p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    else afb_stage_dispatch<L, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+  }
+}
 
 template <int L>
 __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
@@ -94,39 +194,45 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
   const int H = p.H, W = p.W, mode = p.mode, xpitch = p.xpitch;
   const float* xp = p.x + (long long)plane * p.xps;
 
+  // Static per-lane copy schedule: which 16-byte chunks of a stage this lane moves (only the source row
+  // changes from stage to stage).  kind: 0 none, 1 aligned interior (cp.async 16), 2 border / unaligned.
+  int c_soff[C::NCH], c_kind[C::NCH];
+  long long c_goff[C::NCH];
+#pragma unroll
+  for (int k = 0; k < C::NCH; ++k) {
+    const int ch = lane + 32 * k;
+    const int rr = (ch >= C::CPR) ? 1 : 0;
+    const int cc = ch - rr * C::CPR;
+    const int gc = c_a + 4 * cc;
+    c_soff[k] = rr * C::SW + 4 * cc;
+    c_goff[k] = (long long)rr * xpitch + gc;
+    int kind = 0;
+    if (ch < 2 * C::CPR && 4 * cc < need_cols) kind = (vec_ok && gc >= 0 && gc + 3 < W) ? 1 : 2;
+    c_kind[k] = kind;
+  }
+
   auto issue = [&](int t) {
     if (t < n_stage) {
       float* dst = ring + (t & (C::NS - 1)) * (2 * C::SW);
-      const int gr0 = ext_index(r_begin + 2 * t, H, mode);
-      const int gr1 = ext_index(r_begin + 2 * t + 1, H, mode);
-      for (int ch = lane; ch < 2 * C::CPR; ch += 32) {
-        const int rr = (ch >= C::CPR) ? 1 : 0;
-        const int cc = ch - rr * C::CPR;
-        if (4 * cc >= need_cols) continue;
-        const int gr = rr ? gr1 : gr0;
-        float* d = dst + rr * C::SW + 4 * cc;
-        const int gc = c_a + 4 * cc;
-        if (gr < 0) {
-          *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          const float* src = xp + (long long)gr * xpitch;
-          if (vec_ok && gc >= 0 && gc + 3 < W) {
-            cp_async16(d, src + gc);
-          } else {
+      const int r0 = r_begin + 2 * t;
+      if (r0 >= 0 && r0 + 1 < H) {
+        const float* src = xp + (long long)r0 * xpitch;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int g = ext_index(gc + e, W, mode);
-              if (g < 0) d[e] = 0.f;
-              else cp_async4(d + e, src + g);
-            }
+        for (int k = 0; k < C::NCH; ++k) {
+          if (c_kind[k] == 1) cp_async16(dst + c_soff[k], src + c_goff[k]);
+          else if (c_kind[k] == 2) {
+            const int rr = (c_soff[k] >= C::SW) ? 1 : 0;
+            load_chunk_cold(dst + c_soff[k], src + (long long)rr * xpitch, (int)(c_goff[k] - (long long)rr * xpitch), W, mode);
           }
         }
+      } else {
+        load_stage_cold(dst, C::SW, C::CPR, xp, r0, 2, H, W, xpitch, mode, c_a, need_cols, vec_ok, lane);
       }
     }
     cp_async_commit();
   };
 
-#pragma unroll
+#pragma unroll 1
   for (int t = 0; t < C::NS - 1; ++t) issue(t);
 
   float wl[L][2], wh[L][2];
@@ -134,67 +240,20 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
   for (int j = 0; j < L; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
 
   const long long band = (long long)p.Ho * p.Wo;
-  float* ll_base = p.ll + (long long)plane * p.llps + k0 + 2 * lane;
-  float* hi_base = p.highs + (long long)plane * 3 * band + k0 + 2 * lane;
+  float* ll_ptr = p.ll + (long long)plane * p.llps + (long long)ky0 * p.llpitch + k0 + 2 * lane;
+  float* hi_ptr = p.highs + (long long)plane * 3 * band + (long long)ky0 * p.Wo + k0 + 2 * lane;
   const int nv = imax(0, imin(2, p.Wo - (k0 + 2 * lane)));
+  const int llpitch = p.llpitch, Wo = p.Wo;
 
-#pragma unroll C::UNR
+  int uu = 0;
+#pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
     cp_async_wait<C::NS - 2>();
     __syncwarp();
     issue(t + C::NS - 1);
-
     const float* s0 = ring + (t & (C::NS - 1)) * (2 * C::SW) + 4 * lane;
-    float xa[4 * C::NV], xb[4 * C::NV];
-#pragma unroll
-    for (int q = 0; q < C::NV; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(s0 + 4 * q);
-      const float4 b = *reinterpret_cast<const float4*>(s0 + C::SW + 4 * q);
-      xa[4 * q] = a.x; xa[4 * q + 1] = a.y; xa[4 * q + 2] = a.z; xa[4 * q + 3] = a.w;
-      xb[4 * q] = b.x; xb[4 * q + 1] = b.y; xb[4 * q + 2] = b.z; xb[4 * q + 3] = b.w;
-    }
-    // shift the window by two rows, then append the two new row-filtered rows
-#pragma unroll
-    for (int j = 0; j + 2 < L; ++j) {
-      wl[j][0] = wl[j + 2][0]; wl[j][1] = wl[j + 2][1];
-      wh[j][0] = wh[j + 2][0]; wh[j][1] = wh[j + 2][1];
-    }
-#pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      float la = 0.f, ha = 0.f, lb = 0.f, hb = 0.f;
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        const float f0 = p.fw_lo.t[j], f1 = p.fw_hi.t[j];
-        la = fmaf(f0, xa[C::OFF + 2 * o + j], la);
-        ha = fmaf(f1, xa[C::OFF + 2 * o + j], ha);
-        lb = fmaf(f0, xb[C::OFF + 2 * o + j], lb);
-        hb = fmaf(f1, xb[C::OFF + 2 * o + j], hb);
-      }
-      wl[L - 2][o] = la; wh[L - 2][o] = ha;
-      wl[L - 1][o] = lb; wh[L - 1][o] = hb;
-    }
-    if (t >= C::PRO) {
-      const int ky = ky0 + t - C::PRO;
-      float all[2], alh[2], ahl[2], ahh[2];
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < L; ++j) {
-          const float f0 = p.fh_lo.t[j], f1 = p.fh_hi.t[j];
-          a0 = fmaf(f0, wl[j][o], a0);
-          a1 = fmaf(f1, wl[j][o], a1);
-          a2 = fmaf(f0, wh[j][o], a2);
-          a3 = fmaf(f1, wh[j][o], a3);
-        }
-        all[o] = a0; alh[o] = a1; ahl[o] = a2; ahh[o] = a3;
-      }
-      store2(ll_base + (long long)ky * p.llpitch, all[0], all[1], nv, false);
-      float* hr = hi_base + (long long)ky * p.Wo;
-      store2(hr, alh[0], alh[1], nv, true);
-      store2(hr + band, ahl[0], ahl[1], nv, true);
-      store2(hr + 2 * band, ahh[0], ahh[1], nv, true);
-    }
+    afb_stage_dispatch<L, 0>(uu, p, s0, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
   }
   cp_async_wait<0>();
 }
