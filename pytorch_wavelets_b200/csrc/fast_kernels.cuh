@@ -49,27 +49,7 @@ __device__ __noinline__ void load_chunk_cold(float* d, const float* src_row, int
     else cp_async4(d + e, src_row + g);
   }
 }
-// a whole stage of `rows` staged rows, fully general (rows outside the image, unaligned sources ...):
-// used for the few stages that touch the top/bottom border.
-__device__ __noinline__ void load_stage_cold(float* dst, int sw, int cpr, const float* plane, int r0, int rows,
-                                             int H, int W, int pitch, int mode, int c_a, int need_cols,
-                                             int vec_ok, int lane) {
-  for (int ch = lane; ch < rows * cpr; ch += 32) {
-    const int rr = ch / cpr;
-    const int cc = ch - rr * cpr;
-    if (4 * cc >= need_cols) continue;
-    const int gr = ext_index(r0 + rr, H, mode);
-    float* d = dst + rr * sw + 4 * cc;
-    const int gc = c_a + 4 * cc;
-    if (gr < 0) {
-      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      const float* src = plane + (long long)gr * pitch;
-      if (vec_ok && gc >= 0 && gc + 3 < W) cp_async16(d, src + gc);
-      else load_chunk_cold(d, src, gc, W, mode);
-    }
-  }
-}
+__device__ __noinline__ int ext_index_cold(int i, int N, int mode) { return ext_index(i, N, mode); }
 
 // store two adjacent outputs of one lane; nv = how many of them are inside the row (0..2)
 __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, bool stream) {
@@ -97,8 +77,8 @@ struct AfbCfg {
   static constexpr int CPR = SW / 4;                 // 16-byte chunks per staged row
   static constexpr int NCH = (2 * CPR + 31) / 32;    // chunks per lane per stage
   static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
-  static constexpr int WARPS = 4;
-  static constexpr int SMEM_BYTES = WARPS * NS * 2 * SW * 4;
+  static constexpr int NFIX = (4 * (HLA + L) + 31) / 32;  // border fix-ups per lane per stage (2 rows x 2 sides)
+  static constexpr int SMEM_BYTES = NS * 2 * SW * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
   static constexpr int UNR = L / 2;                  // window period: stage copies in the unrolled loop
 };
@@ -170,19 +150,17 @@ __device__ __forceinline__ void afb_stage_dispatch(int uu, const AfbParams& p, c
 }
 
 template <int L>
-__global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
-                                                    int CH, int vec_ok) {
+__global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
+                                                   int CH) {
   using C = AfbCfg<L>;
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long item = (long long)blockIdx.x * C::WARPS + warp;
-  if (item >= (long long)p.planes * n_strips * n_chunks) return;  // whole warp leaves; no CTA barriers below
+  extern __shared__ __align__(16) float ring[];  // this warp's staging ring: NS stages x 2 rows x SW floats
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
   const int strip = (int)(item % n_strips);
   item /= n_strips;
   const int chunk = (int)(item % n_chunks);
   const int plane = (int)(item / n_chunks);
 
-  float* ring = smem + warp * (C::NS * 2 * C::SW);
   const int k0 = strip * 64;
   const int ky0 = chunk * CH;
   const int ky1 = imin(ky0 + CH, p.Ho);
@@ -194,10 +172,38 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
   const int H = p.H, W = p.W, mode = p.mode, xpitch = p.xpitch;
   const float* xp = p.x + (long long)plane * p.xps;
 
-  // Static per-lane copy schedule: which 16-byte chunks of a stage this lane moves (only the source row
-  // changes from stage to stage).  kind: 0 none, 1 aligned interior (cp.async 16), 2 border / unaligned.
-  int c_soff[C::NCH], c_kind[C::NCH];
-  long long c_goff[C::NCH];
+  // ---- static per-lane schedule (computed once; only the source rows change from stage to stage) ----
+  // (a) border fix-ups: staged columns outside the image are filled from the staged copy of the column the
+  //     boundary extension maps them to (or with zeros) after the stage has landed -- two shared-memory
+  //     accesses instead of an element-wise global gather.  Possible when that source column is staged too.
+  const int nleft = imin(imax(0, -c_a), need_cols);
+  const int sr0 = imax(W - c_a, 0);                   // first staged column right of the image
+  const int nright = imax(0, need_cols - sr0);
+  const int nb_row = nleft + nright;
+  int fix_dst[C::NFIX], fix_src[C::NFIX];
+  bool bad = (2 * nb_row > 32 * C::NFIX);
+#pragma unroll
+  for (int q = 0; q < C::NFIX; ++q) {
+    fix_dst[q] = -1;
+    fix_src[q] = -1;
+    const int e = lane + 32 * q;
+    if (e < 2 * nb_row) {
+      const int rr = (e >= nb_row) ? 1 : 0;
+      const int idx = e - rr * nb_row;
+      const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
+      const int g = ext_index(c_a + sidx, W, mode);
+      fix_dst[q] = rr * C::SW + sidx;
+      if (g >= 0) {
+        const int ss = g - c_a;
+        if (ss < 0 || ss >= need_cols) bad = true;
+        fix_src[q] = rr * C::SW + ss;
+      }
+    }
+  }
+  const bool use_cold = __any_sync(0xffffffffu, bad);   // e.g. 'periodic': the source is in another strip
+  const bool any_fix = (nb_row > 0) && !use_cold;
+  // (b) copy schedule: kind 0 nothing, 1 aligned 16-byte cp.async, 2 element-wise (only when use_cold)
+  int c_soff[C::NCH], c_gcol[C::NCH], c_kind[C::NCH];
 #pragma unroll
   for (int k = 0; k < C::NCH; ++k) {
     const int ch = lane + 32 * k;
@@ -205,28 +211,38 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
     const int cc = ch - rr * C::CPR;
     const int gc = c_a + 4 * cc;
     c_soff[k] = rr * C::SW + 4 * cc;
-    c_goff[k] = (long long)rr * xpitch + gc;
+    c_gcol[k] = gc;
     int kind = 0;
-    if (ch < 2 * C::CPR && 4 * cc < need_cols) kind = (vec_ok && gc >= 0 && gc + 3 < W) ? 1 : 2;
-    c_kind[k] = kind;
+    if (ch < 2 * C::CPR && 4 * cc < need_cols) {
+      const bool inside = (gc >= 0 && gc + 3 < W);
+      const bool partly = (gc + 3 >= 0 && gc < W);
+      // a chunk straddling the right edge may be read whole: the row pitch covers it (launcher guarantees)
+      if (inside || (partly && gc >= 0 && gc + 3 < xpitch && !use_cold)) kind = 1;
+      else if (use_cold) kind = 2;
+    }
+    c_kind[k] = kind | (rr << 2);
   }
 
   auto issue = [&](int t) {
     if (t < n_stage) {
       float* dst = ring + (t & (C::NS - 1)) * (2 * C::SW);
       const int r0 = r_begin + 2 * t;
-      if (r0 >= 0 && r0 + 1 < H) {
-        const float* src = xp + (long long)r0 * xpitch;
+      const int gr0 = ((unsigned)r0 < (unsigned)H) ? r0 : ext_index_cold(r0, H, mode);
+      const int gr1 = ((unsigned)(r0 + 1) < (unsigned)H) ? r0 + 1 : ext_index_cold(r0 + 1, H, mode);
+      const float* src0 = xp + (long long)gr0 * xpitch;
+      const float* src1 = xp + (long long)gr1 * xpitch;
 #pragma unroll
-        for (int k = 0; k < C::NCH; ++k) {
-          if (c_kind[k] == 1) cp_async16(dst + c_soff[k], src + c_goff[k]);
-          else if (c_kind[k] == 2) {
-            const int rr = (c_soff[k] >= C::SW) ? 1 : 0;
-            load_chunk_cold(dst + c_soff[k], src + (long long)rr * xpitch, (int)(c_goff[k] - (long long)rr * xpitch), W, mode);
-          }
+      for (int k = 0; k < C::NCH; ++k) {
+        const int kind = c_kind[k] & 3;
+        if (kind != 0) {
+          const bool rr = (c_kind[k] & 4) != 0;
+          const int gr = rr ? gr1 : gr0;
+          const float* src = rr ? src1 : src0;
+          float* d = dst + c_soff[k];
+          if (gr < 0) *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+          else if (kind == 1) cp_async16(d, src + c_gcol[k]);
+          else load_chunk_cold(d, src, c_gcol[k], W, mode);
         }
-      } else {
-        load_stage_cold(dst, C::SW, C::CPR, xp, r0, 2, H, W, xpitch, mode, c_a, need_cols, vec_ok, lane);
       }
     }
     cp_async_commit();
@@ -250,9 +266,15 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
   for (int t = 0; t < n_stage; ++t) {
     cp_async_wait<C::NS - 2>();
     __syncwarp();
+    float* stage = ring + (t & (C::NS - 1)) * (2 * C::SW);
+    if (any_fix) {
+#pragma unroll
+      for (int q = 0; q < C::NFIX; ++q)
+        if (fix_dst[q] >= 0) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
+      __syncwarp();
+    }
     issue(t + C::NS - 1);
-    const float* s0 = ring + (t & (C::NS - 1)) * (2 * C::SW) + 4 * lane;
-    afb_stage_dispatch<L, 0>(uu, p, s0, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    afb_stage_dispatch<L, 0>(uu, p, stage + 4 * lane, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
   }
   cp_async_wait<0>();
@@ -261,9 +283,12 @@ __global__ void __launch_bounds__(128) afb2d_stream(const __grid_constant__ AfbP
 template <int L>
 inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
   using C = AfbCfg<L>;
+  // aligned 16-byte staging needs an aligned source; anything else takes the generic kernel
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && (p.xpitch % 4 == 0) && (p.xps % 4 == 0);
+  if (!vec_ok) return kNoFastPath;
   const int n_strips = (p.Wo + 63) / 64;
   // enough independent warps to fill the machine several times over; otherwise split the rows
-  const long long want = 148LL * 20 * 3;
+  const long long want = 148LL * 32 * 3;
   const long long base = (long long)p.planes * n_strips;
   int n_chunks = 1;
   if (base < want) {
@@ -274,12 +299,10 @@ inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
   }
   const int CH = (p.Ho + n_chunks - 1) / n_chunks;
   n_chunks = (p.Ho + CH - 1) / CH;
-  const int vec_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && (p.xpitch % 4 == 0) && (p.xps % 4 == 0);
-  const long long items = base * n_chunks;
-  const long long blocks = (items + C::WARPS - 1) / C::WARPS;
+  const long long blocks = base * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
-  afb2d_stream<L><<<(unsigned)blocks, 32 * C::WARPS, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, vec_ok);
+  afb2d_stream<L><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
   return 0;
 }
 
