@@ -158,6 +158,8 @@ int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr, int N,
   DtParams p;
   int rc = build_scat_j1(p, x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias);
   if (rc) return rc;
+  rc = fast::try_launch_scat_j1(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
   return launch_tile(k_scat_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj1_smem_floats(L0, L1), stream);
 }
 

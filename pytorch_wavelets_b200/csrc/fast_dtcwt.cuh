@@ -1,0 +1,404 @@
+// fast_dtcwt.cuh -- streaming DTCWT forward kernels (included inside namespace b200w::fast by
+// fast_kernels.cuh).  Same machinery as the DWT kernel: per-warp strip, cp.async ring (StripLoader),
+// 128/64-bit conflict-free LDS for the pass along W, rotating register window for the pass along H,
+// taps from the constant bank, q2c (or the ScatLayer magnitude) applied in registers before the store.
+
+// store one complex number (re, im) of orientation slot `o` for this lane
+__device__ __forceinline__ void store_cplx(float* hq, long long so, long long sr, bool vec, int o, float re, float im) {
+  float* q = hq + o * so;
+  if (vec) __stcs(reinterpret_cast<float2*>(q), make_float2(re, im));
+  else { __stcs(q, re); __stcs(q + sr, im); }
+}
+
+// q2c of one real subband quad (a b / c d) into orientation slots o1 (w1) and o2 (w2)
+__device__ __forceinline__ void q2c_emit(float a, float b, float c, float d, float* hq, long long so, long long sr,
+                                         bool vec, int o1, int o2) {
+  a = __fmul_rn(a, kInvSqrt2); b = __fmul_rn(b, kInvSqrt2);
+  c = __fmul_rn(c, kInvSqrt2); d = __fmul_rn(d, kInvSqrt2);
+  store_cplx(hq, so, sr, vec, o1, __fsub_rn(a, d), __fadd_rn(b, c));
+  store_cplx(hq, so, sr, vec, o2, __fadd_rn(a, d), __fsub_rn(b, c));
+}
+
+// ScatLayer epilogue for one subband quad: smoothed magnitudes of w1 / w2 (+ optional re/r, im/r)
+__device__ __forceinline__ void scat_emit(float a, float b, float c, float d, const DtParams& p, long long zbase,
+                                          long long dbase, long long ostride, int o1, int o2) {
+  a = __fmul_rn(a, kInvSqrt2); b = __fmul_rn(b, kInvSqrt2);
+  c = __fmul_rn(c, kInvSqrt2); d = __fmul_rn(d, kInvSqrt2);
+  const float re[2] = {__fsub_rn(a, d), __fadd_rn(a, d)};
+  const float im[2] = {__fadd_rn(b, c), __fsub_rn(b, c)};
+  const int os[2] = {o1, o2};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float rr = __fmul_rn(re[k], re[k]), ii = __fmul_rn(im[k], im[k]);
+    const float r = __fsqrt_rn(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
+    __stcs(p.z + zbase + (1 + os[k]) * ostride, __fsub_rn(r, p.magbias));
+    if (p.dre) {
+      __stcs(p.dre + dbase + os[k] * ostride, __fdiv_rn(re[k], r));
+      __stcs(p.dim + dbase + os[k] * ostride, __fdiv_rn(im[k], r));
+    }
+  }
+}
+
+// ================================================================================================
+// K3 / K7 fast: DTCWT level-1 forward (odd filter lengths L0, L1), optional ScatLayer epilogue.
+//   strip = 64 columns per warp (2 per lane); stage = 2 image rows = one row of 2x2 quads.
+// ================================================================================================
+template <int L0, int L1>
+struct J1Cfg {
+  static constexpr int M0 = L0 / 2, M1 = L1 / 2, M = (M0 > M1) ? M0 : M1;
+  static constexpr int HLA = (M + 3) / 4 * 4;
+  static constexpr int SW = HLA + 64 + HLA;
+  static constexpr int OFFX = HLA - M;              // staged index of column (c - M) for the lane's first column
+  static constexpr int NX = OFFX + 2 * M + 2;       // floats a lane needs per row, from its aligned 8-byte base
+  static constexpr int NV2 = (NX + 1) / 2;          // ... as 64-bit loads
+  static constexpr int WR = 2 * M + 2;              // register window rows
+  static constexpr int UNR = M + 1;                 // window period in stages
+  static constexpr int PRO = M;
+  static constexpr int NS = 4;
+  static constexpr int NFIX = (2 * 2 * HLA + 31) / 32;
+  static constexpr int SMEM_BYTES = NS * 2 * SW * 4;
+  using Loader = StripLoader<2, SW, NS, NFIX>;
+};
+
+template <int L0, int L1, bool SCAT, int U>
+__device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, float (&wl)[J1Cfg<L0, L1>::WR][2],
+                                         float (&wh)[J1Cfg<L0, L1>::WR][2], bool emit, float*& ll_ptr, float*& hq,
+                                         long long& zoff, bool colvalid, bool vec, long long zplane, long long dplane,
+                                         long long ostride) {
+  using C = J1Cfg<L0, L1>;
+  constexpr int WR = C::WR;
+  // row pass on the two staged rows
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float x[2 * C::NV2];
+#pragma unroll
+    for (int q = 0; q < C::NV2; ++q) {
+      const float2 v = *reinterpret_cast<const float2*>(s0 + r * C::SW + 2 * q);
+      x[2 * q] = v.x; x[2 * q + 1] = v.y;
+    }
+    const int S = (2 * U + r) % WR;
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float lo = 0.f, hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < L0; ++j) lo = fmaf(p.f0.t[j], x[C::OFFX + o + (C::M - C::M0) + j], lo);
+#pragma unroll
+      for (int j = 0; j < L1; ++j) hi = fmaf(p.f1.t[j], x[C::OFFX + o + (C::M - C::M1) + j], hi);
+      wl[S][o] = lo;
+      wh[S][o] = hi;
+    }
+  }
+  if (emit) {
+    float vll[2][2], vlh[2][2], vhl[2][2], vhh[2][2];  // [dr][o]
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+#pragma unroll
+        for (int j = 0; j < L0; ++j) {
+          const int sl = (2 * U + dr - C::M - C::M0 + j + 4 * WR) % WR;
+          a = fmaf(p.f0.t[j], wl[sl][o], a);
+          c = fmaf(p.f0.t[j], wh[sl][o], c);
+        }
+#pragma unroll
+        for (int j = 0; j < L1; ++j) {
+          const int sl = (2 * U + dr - C::M - C::M1 + j + 4 * WR) % WR;
+          b = fmaf(p.f1.t[j], wl[sl][o], b);
+          d = fmaf(p.f1.t[j], wh[sl][o], d);
+        }
+        vll[dr][o] = a; vlh[dr][o] = b; vhl[dr][o] = c; vhh[dr][o] = d;
+      }
+    if (colvalid) {
+      if (!SCAT) {
+        store2(ll_ptr, vll[0][0], vll[0][1], 2, false);
+        store2(ll_ptr + p.outpitch, vll[1][0], vll[1][1], 2, false);
+        if (p.highs) {
+          const long long so = p.hs[2], sr = p.hs[5];
+          q2c_emit(vlh[0][0], vlh[0][1], vlh[1][0], vlh[1][1], hq, so, sr, vec, 0, 5);  // lh -> 15, 165
+          q2c_emit(vhh[0][0], vhh[0][1], vhh[1][0], vhh[1][1], hq, so, sr, vec, 1, 4);  // hh -> 45, 135
+          q2c_emit(vhl[0][0], vhl[0][1], vhl[1][0], vhl[1][1], hq, so, sr, vec, 2, 3);  // hl -> 75, 105
+        }
+      } else {
+        float s = __fadd_rn(vll[0][0], vll[0][1]);
+        s = __fadd_rn(s, vll[1][0]);
+        s = __fadd_rn(s, vll[1][1]);
+        __stcs(p.z + zplane + zoff, __fmul_rn(s, 0.25f));
+        scat_emit(vlh[0][0], vlh[0][1], vlh[1][0], vlh[1][1], p, zplane + zoff, dplane + zoff, ostride, 0, 5);
+        scat_emit(vhh[0][0], vhh[0][1], vhh[1][0], vhh[1][1], p, zplane + zoff, dplane + zoff, ostride, 1, 4);
+        scat_emit(vhl[0][0], vhl[0][1], vhl[1][0], vhl[1][1], p, zplane + zoff, dplane + zoff, ostride, 2, 3);
+      }
+    }
+    ll_ptr += 2 * p.outpitch;
+    hq += p.hs[3];
+    zoff += (p.W >> 1);
+  }
+}
+
+template <int L0, int L1, bool SCAT, int U>
+__device__ __forceinline__ void j1_dispatch(int uu, const DtParams& p, const float* s0,
+                                            float (&wl)[J1Cfg<L0, L1>::WR][2], float (&wh)[J1Cfg<L0, L1>::WR][2],
+                                            bool emit, float*& ll_ptr, float*& hq, long long& zoff, bool colvalid,
+                                            bool vec, long long zplane, long long dplane, long long ostride) {
+  if constexpr (U < J1Cfg<L0, L1>::UNR) {
+    if (uu == U) j1_stage<L0, L1, SCAT, U>(p, s0, wl, wh, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
+    else j1_dispatch<L0, L1, SCAT, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
+  }
+}
+
+template <int L0, int L1, bool SCAT>
+__global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+                                                    int CH /* quad rows per chunk */) {
+  using C = J1Cfg<L0, L1>;
+  extern __shared__ __align__(16) float ring[];
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+  const int n = plane / p.C, ch = plane - n * p.C;
+
+  const int c0 = strip * 64;
+  const int qy0 = chunk * CH;
+  const int qy1 = imin(qy0 + CH, p.H >> 1);
+  const int n_stage = (qy1 - qy0) + C::PRO;
+  const int ncols = imin(64, p.W - c0);
+
+  typename C::Loader ld;
+  ld.init(ring, p.in + (long long)plane * p.inps, p.H, p.W, p.inpitch, p.sym ? B200W_MODE_SYMMETRIC : B200W_MODE_ZERO,
+          c0 - C::HLA, C::HLA + ncols + C::M, 2 * qy0 - C::M, n_stage, lane);
+  ld.prologue();
+
+  float wl[C::WR][2], wh[C::WR][2];
+#pragma unroll
+  for (int j = 0; j < C::WR; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+
+  const bool colvalid = (c0 + 2 * lane) < p.W;
+  const int h2 = p.H >> 1, w2 = p.W >> 1;
+  float* ll_ptr = SCAT ? nullptr : p.out + (long long)plane * p.outps + (long long)(2 * qy0) * p.outpitch + c0 + 2 * lane;
+  float* hq = nullptr;
+  bool vec = false;
+  if (!SCAT && p.highs) {
+    hq = p.highs + n * p.hs[0] + ch * p.hs[1] + (long long)qy0 * p.hs[3] + (long long)((c0 >> 1) + lane) * p.hs[4];
+    vec = (p.hs[5] == 1) && ((p.hs[4] & 1) == 0) && ((p.hs[3] & 1) == 0) && ((p.hs[2] & 1) == 0) &&
+          ((p.hs[1] & 1) == 0) && ((p.hs[0] & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.highs) & 7) == 0);
+  }
+  // scat: z is (N,7,C,h2,w2), dre/dim (N,6,C,h2,w2); orientation stride = C*h2*w2
+  const long long ostride = (long long)p.C * h2 * w2;
+  const long long zplane = ((long long)n * 7 * p.C + ch) * h2 * w2;
+  const long long dplane = ((long long)n * 6 * p.C + ch) * h2 * w2;
+  long long zoff = (long long)qy0 * w2 + (c0 >> 1) + lane;
+
+  int uu = 0;
+#pragma unroll 1
+  for (int t = 0; t < n_stage; ++t) {
+    const float* stage = ld.acquire(t);
+    ld.issue(t + C::NS - 1);
+    j1_dispatch<L0, L1, SCAT, 0>(uu, p, stage + 2 * lane, wl, wh, t >= C::PRO, ll_ptr, hq, zoff, colvalid, vec, zplane,
+                                 dplane, ostride);
+    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <int L0, int L1, bool SCAT>
+inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
+  using C = J1Cfg<L0, L1>;
+  if (!aligned_plane(p.in, p.inps, p.inpitch)) return kNoFastPath;
+  if (!SCAT && (p.outpitch & 1)) return kNoFastPath;
+  const int n_strips = (p.W + 63) / 64;
+  const long long planes = (long long)p.N * p.C;
+  int n_chunks, CH;
+  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  const long long blocks = planes * n_strips * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return kNoFastPath;
+  fwd_j1_stream<L0, L1, SCAT><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
+  return 0;
+}
+
+template <bool SCAT>
+inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
+  if (g_force_generic) return kNoFastPath;
+  if (!SCAT && !p.highs) return kNoFastPath;  // skip_hps: low-pass only, generic kernel
+  if ((long long)p.N * p.C == 0) return 0;
+  if (p.L0 == 5 && p.L1 == 7) return launch_j1_stream<5, 7, SCAT>(p, stream);   // near_sym_a analysis
+  if (p.L0 == 7 && p.L1 == 5) return launch_j1_stream<7, 5, SCAT>(p, stream);   // near_sym_a synthesis (backward)
+  if (p.L0 == 9 && p.L1 == 7) return launch_j1_stream<9, 7, SCAT>(p, stream);   // antonini
+  if (p.L0 == 5 && p.L1 == 3) return launch_j1_stream<5, 3, SCAT>(p, stream);   // legall
+  if (p.L0 == 13 && p.L1 == 19) return launch_j1_stream<13, 19, SCAT>(p, stream);  // near_sym_b
+  return kNoFastPath;
+}
+inline int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<false>(p, stream); }
+inline int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<true>(p, stream); }
+
+// ================================================================================================
+// K4 fast: DTCWT level >= 2 forward, q-shift filters of even length MQ.
+//   lane = one output complex column q: 4 input columns -> 2 half-resolution columns;
+//   strip = 32 q = 128 input columns; stage = 4 input rows = 2 half-resolution rows = 1 quad row.
+//   taps: f0=h0a f1=h1a f2=h0b f3=h1b (stored).
+// ================================================================================================
+template <int MQ>
+struct J2Cfg {
+  static constexpr int HL = MQ - 2;
+  static constexpr int HLA = (HL + 3) / 4 * 4;
+  static constexpr int SW = HLA + 128 + HLA;
+  static constexpr int OFF = HLA - HL;
+  static constexpr int NX = OFF + 2 * MQ;
+  static constexpr int NV = (NX + 3) / 4;
+  static constexpr int WR = 2 * MQ;
+  static constexpr int UNR = MQ / 2;
+  static constexpr int PRO = (MQ - 2) / 2;
+  static constexpr int NS = 3;
+  static constexpr int NFIX = (4 * 2 * HLA + 31) / 32;
+  static constexpr int SMEM_BYTES = NS * 4 * SW * 4;
+  using Loader = StripLoader<4, SW, NS, NFIX>;
+};
+
+template <int MQ, int U>
+__device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, float (&wl)[2 * MQ][2],
+                                         float (&wh)[2 * MQ][2], bool emit, bool want_hi, float*& ll_ptr, float*& hq,
+                                         bool qvalid, bool vec) {
+  using C = J2Cfg<MQ>;
+  constexpr int WR = C::WR;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float x[4 * C::NV];
+#pragma unroll
+    for (int q = 0; q < C::NV; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(s0 + r * C::SW + 4 * q);
+      x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+    float la = 0.f, lb = 0.f, ha = 0.f, hb = 0.f;
+#pragma unroll
+    for (int j = 0; j < MQ; ++j) {
+      const float ve = x[C::OFF + 2 * j], vo = x[C::OFF + 2 * j + 1];
+      la = fmaf(p.f2.t[j], ve, la);  // Ya with h0b
+      lb = fmaf(p.f0.t[j], vo, lb);  // Yb with h0a
+      ha = fmaf(p.f3.t[j], ve, ha);  // Ya with h1b
+      hb = fmaf(p.f1.t[j], vo, hb);  // Yb with h1a
+    }
+    const int S = (4 * U + r) % WR;
+    wl[S][0] = la; wl[S][1] = lb;   // low-pass interleave (a, b)
+    wh[S][0] = hb; wh[S][1] = ha;   // high-pass interleave (b, a)
+  }
+  if (emit) {
+    float vll[2][2], vlh[2][2], vhl[2][2], vhh[2][2];  // [half-res row 0/1][half-res col 0/1]
+#pragma unroll
+    for (int dc = 0; dc < 2; ++dc) {
+      float ll0 = 0.f, ll1 = 0.f, lh0 = 0.f, lh1 = 0.f, hl0 = 0.f, hl1 = 0.f, hh0 = 0.f, hh1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < MQ; ++j) {
+        const int sa = (4 * U + 4 + 2 * j) % WR, sb = (4 * U + 5 + 2 * j) % WR;
+        const float le = wl[sa][dc], lo_ = wl[sb][dc], he = wh[sa][dc], ho = wh[sb][dc];
+        ll0 = fmaf(p.f2.t[j], le, ll0);   // ll[2q]   = Ya(h0b) on lo
+        ll1 = fmaf(p.f0.t[j], lo_, ll1);  // ll[2q+1] = Yb(h0a)
+        lh0 = fmaf(p.f1.t[j], lo_, lh0);  // lh[2q]   = Yb(h1a)   (high-pass interleave)
+        lh1 = fmaf(p.f3.t[j], le, lh1);   // lh[2q+1] = Ya(h1b)
+        hl0 = fmaf(p.f2.t[j], he, hl0);
+        hl1 = fmaf(p.f0.t[j], ho, hl1);
+        hh0 = fmaf(p.f1.t[j], ho, hh0);
+        hh1 = fmaf(p.f3.t[j], he, hh1);
+      }
+      vll[0][dc] = ll0; vll[1][dc] = ll1; vlh[0][dc] = lh0; vlh[1][dc] = lh1;
+      vhl[0][dc] = hl0; vhl[1][dc] = hl1; vhh[0][dc] = hh0; vhh[1][dc] = hh1;
+    }
+    if (qvalid) {
+      store2(ll_ptr, vll[0][0], vll[0][1], 2, false);
+      store2(ll_ptr + p.outpitch, vll[1][0], vll[1][1], 2, false);
+      if (want_hi) {
+        const long long so = p.hs[2], sr = p.hs[5];
+        q2c_emit(vlh[0][0], vlh[0][1], vlh[1][0], vlh[1][1], hq, so, sr, vec, 0, 5);
+        q2c_emit(vhh[0][0], vhh[0][1], vhh[1][0], vhh[1][1], hq, so, sr, vec, 1, 4);
+        q2c_emit(vhl[0][0], vhl[0][1], vhl[1][0], vhl[1][1], hq, so, sr, vec, 2, 3);
+      }
+    }
+    ll_ptr += 2 * p.outpitch;
+    hq += p.hs[3];
+  }
+}
+
+template <int MQ, int U>
+__device__ __forceinline__ void j2_dispatch(int uu, const DtParams& p, const float* s0, float (&wl)[2 * MQ][2],
+                                            float (&wh)[2 * MQ][2], bool emit, bool want_hi, float*& ll_ptr,
+                                            float*& hq, bool qvalid, bool vec) {
+  if constexpr (U < J2Cfg<MQ>::UNR) {
+    if (uu == U) j2_stage<MQ, U>(p, s0, wl, wh, emit, want_hi, ll_ptr, hq, qvalid, vec);
+    else j2_dispatch<MQ, U + 1>(uu, p, s0, wl, wh, emit, want_hi, ll_ptr, hq, qvalid, vec);
+  }
+}
+
+template <int MQ>
+__global__ void __launch_bounds__(32) fwd_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+                                                        int n_chunks, int CH /* quad rows per chunk */) {
+  using C = J2Cfg<MQ>;
+  extern __shared__ __align__(16) float ring[];
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+  const int n = plane / p.C, ch = plane - n * p.C;
+
+  const int q0 = strip * 32;
+  const int Q = p.W >> 2;
+  const int qy0 = chunk * CH;
+  const int qy1 = imin(qy0 + CH, p.H >> 2);
+  const int n_stage = (qy1 - qy0) + C::PRO;
+  const int nq = imin(32, Q - q0);
+
+  typename C::Loader ld;
+  ld.init(ring, p.in + (long long)plane * p.inps, p.H, p.W, p.inpitch, B200W_MODE_SYMMETRIC, 4 * q0 - C::HLA,
+          C::HLA + 4 * nq + C::HL, 4 * qy0 + 2 - MQ, n_stage, lane);
+  ld.prologue();
+
+  float wl[C::WR][2], wh[C::WR][2];
+#pragma unroll
+  for (int j = 0; j < C::WR; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+
+  const bool qvalid = (q0 + lane) < Q;
+  const bool want_hi = (p.highs != nullptr);
+  float* ll_ptr = p.out + (long long)plane * p.outps + (long long)(2 * qy0) * p.outpitch + 2 * (q0 + lane);
+  float* hq = nullptr;
+  bool vec = false;
+  if (want_hi) {
+    hq = p.highs + n * p.hs[0] + ch * p.hs[1] + (long long)qy0 * p.hs[3] + (long long)(q0 + lane) * p.hs[4];
+    vec = (p.hs[5] == 1) && ((p.hs[4] & 1) == 0) && ((p.hs[3] & 1) == 0) && ((p.hs[2] & 1) == 0) &&
+          ((p.hs[1] & 1) == 0) && ((p.hs[0] & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.highs) & 7) == 0);
+  }
+
+  int uu = 0;
+#pragma unroll 1
+  for (int t = 0; t < n_stage; ++t) {
+    const float* stage = ld.acquire(t);
+    ld.issue(t + C::NS - 1);
+    j2_dispatch<MQ, 0>(uu, p, stage + 4 * lane, wl, wh, t >= C::PRO, want_hi, ll_ptr, hq, qvalid, vec);
+    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <int MQ>
+inline int launch_j2_stream(const DtParams& p, cudaStream_t stream) {
+  using C = J2Cfg<MQ>;
+  if (!aligned_plane(p.in, p.inps, p.inpitch)) return kNoFastPath;
+  if (p.outpitch & 1) return kNoFastPath;
+  const int n_strips = ((p.W >> 2) + 31) / 32;
+  const long long planes = (long long)p.N * p.C;
+  int n_chunks, CH;
+  pick_chunks(planes * n_strips, p.H >> 2, 4, &n_chunks, &CH);
+  const long long blocks = planes * n_strips * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return kNoFastPath;
+  fwd_j2plus_stream<MQ><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
+  return 0;
+}
+
+inline int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream) {
+  if (g_force_generic) return kNoFastPath;
+  if ((long long)p.N * p.C == 0) return 0;
+  if (p.L0 == 10) return launch_j2_stream<10>(p, stream);  // qshift_a, qshift_06
+  return kNoFastPath;
+}

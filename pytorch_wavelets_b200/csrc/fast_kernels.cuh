@@ -40,16 +40,139 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // Boundary handling stays out of line: the hot loop must fit the instruction cache (an inlined
 // ext_index drags three integer modulo sequences per call into every unrolled stage).
-// one 4-float chunk that touches the image border (or an unaligned source): element-wise remap
-__device__ __noinline__ void load_chunk_cold(float* d, const float* src_row, int gc, int W, int mode) {
-#pragma unroll 1
-  for (int e = 0; e < 4; ++e) {
-    const int g = ext_index(gc + e, W, mode);
-    if (g < 0) d[e] = 0.f;
-    else cp_async4(d + e, src_row + g);
+__device__ __noinline__ int ext_index_cold(int i, int N, int mode) { return ext_index(i, N, mode); }
+
+// General (rare) stage load: rows outside the image (remapped or zero-filled) and, when `elementwise`,
+// border columns gathered element by element.  Used for the few stages that touch the top/bottom border
+// and for extension modes whose source column is not inside the strip (e.g. 'periodic').
+__device__ __noinline__ void load_stage_general(float* dst, int rows, int sw, int cpr, const float* plane, int r0,
+                                                int H, int W, int pitch, int mode, int c_a, int need_cols,
+                                                int elementwise, int lane) {
+  for (int ch = lane; ch < rows * cpr; ch += 32) {
+    const int rr = ch / cpr;
+    const int cc = ch - rr * cpr;
+    if (4 * cc >= need_cols) continue;
+    const int gr = ext_index(r0 + rr, H, mode);
+    float* d = dst + rr * sw + 4 * cc;
+    const int gc = c_a + 4 * cc;
+    if (gr < 0) {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float* src = plane + (long long)gr * pitch;
+    const bool inside = (gc >= 0 && gc + 3 < W);
+    if (inside || (!elementwise && gc >= 0 && gc < W && gc + 3 < pitch)) {
+      cp_async16(d, src + gc);
+    } else if (elementwise) {
+      for (int e = 0; e < 4; ++e) {
+        const int g = ext_index(gc + e, W, mode);
+        if (g < 0) d[e] = 0.f;
+        else cp_async4(d + e, src + g);
+      }
+    }
   }
 }
-__device__ __noinline__ int ext_index_cold(int i, int N, int mode) { return ext_index(i, N, mode); }
+
+// ================================================================================================
+// StripLoader: per-warp staging of a vertical strip, ROWS image rows per stage, ring of NS stages.
+//   - static per-lane copy schedule (aligned 16-byte cp.async.cg), computed once;
+//   - columns outside the image are filled after landing from the staged copy of the column the
+//     extension maps them to ("fix-ups": one LDS + one STS per border element);
+//   - rows outside the image / exotic modes go through load_stage_general (out of line).
+// The caller guarantees: plane base 16-byte aligned, pitch % 4 == 0, c_a % 4 == 0, SW % 4 == 0.
+// ================================================================================================
+template <int ROWS, int SW, int NS, int NFIX>
+struct StripLoader {
+  static constexpr int CPR = SW / 4;
+  static constexpr int NCH = (ROWS * CPR + 31) / 32;
+  static constexpr int STAGE = ROWS * SW;  // floats per stage
+
+  float* ring;
+  const float* plane;
+  int H, W, pitch, mode, c_a, need_cols, r_begin, n_stage, lane;
+  bool use_cold, any_fix;
+  int c_soff[NCH];
+  long long c_goff[NCH];
+  bool c_on[NCH];
+  int fix_dst[NFIX], fix_src[NFIX];
+
+  __device__ __forceinline__ void init(float* ring_, const float* plane_, int H_, int W_, int pitch_, int mode_,
+                                       int c_a_, int need_cols_, int r_begin_, int n_stage_, int lane_) {
+    ring = ring_; plane = plane_; H = H_; W = W_; pitch = pitch_; mode = mode_; c_a = c_a_;
+    need_cols = need_cols_; r_begin = r_begin_; n_stage = n_stage_; lane = lane_;
+    const int nleft = imin(imax(0, -c_a), need_cols);
+    const int sr0 = imax(W - c_a, 0);  // first staged column right of the image
+    const int nright = imax(0, need_cols - sr0);
+    const int nb_row = nleft + nright;
+    bool bad = (ROWS * nb_row > 32 * NFIX);
+#pragma unroll
+    for (int q = 0; q < NFIX; ++q) {
+      fix_dst[q] = -1;
+      fix_src[q] = -1;
+      const int e = lane + 32 * q;
+      if (e < ROWS * nb_row) {
+        const int rr = e / (nb_row > 0 ? nb_row : 1);
+        const int idx = e - rr * nb_row;
+        const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
+        const int g = ext_index(c_a + sidx, W, mode);
+        fix_dst[q] = rr * SW + sidx;
+        if (g >= 0) {
+          const int ss = g - c_a;
+          if (ss < 0 || ss >= need_cols) bad = true;
+          fix_src[q] = rr * SW + ss;
+        }
+      }
+    }
+    use_cold = __any_sync(0xffffffffu, bad);
+    any_fix = (nb_row > 0) && !use_cold;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = lane + 32 * k;
+      const int rr = ch / CPR;
+      const int cc = ch - rr * CPR;
+      const int gc = c_a + 4 * cc;
+      c_soff[k] = rr * SW + 4 * cc;
+      c_goff[k] = (long long)rr * pitch + gc;
+      // a chunk straddling the right edge is read whole: the row pitch covers it
+      c_on[k] = (ch < ROWS * CPR) && (4 * cc < need_cols) && (gc >= 0) && (gc < W) && (gc + 3 < pitch);
+    }
+  }
+
+  __device__ __forceinline__ void issue(int t) {
+    if (t < n_stage) {
+      float* dst = ring + (t % NS) * STAGE;
+      const int r0 = r_begin + ROWS * t;
+      if (!use_cold && r0 >= 0 && r0 + ROWS <= H) {
+        const float* src = plane + (long long)r0 * pitch;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (c_on[k]) cp_async16(dst + c_soff[k], src + c_goff[k]);
+      } else {
+        load_stage_general(dst, ROWS, SW, CPR, plane, r0, H, W, pitch, mode, c_a, need_cols, use_cold ? 1 : 0, lane);
+      }
+    }
+    cp_async_commit();
+  }
+
+  __device__ __forceinline__ void prologue() {
+#pragma unroll 1
+    for (int t = 0; t < NS - 1; ++t) issue(t);
+  }
+
+  // wait for stage t, make it visible to the warp, patch the border columns; returns the stage base
+  __device__ __forceinline__ float* acquire(int t) {
+    cp_async_wait<NS - 2>();
+    __syncwarp();
+    float* stage = ring + (t % NS) * STAGE;
+    if (any_fix) {
+#pragma unroll
+      for (int q = 0; q < NFIX; ++q)
+        if (fix_dst[q] >= 0) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
+      __syncwarp();
+    }
+    return stage;
+  }
+};
 
 // store two adjacent outputs of one lane; nv = how many of them are inside the row (0..2)
 __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, bool stream) {
@@ -60,6 +183,26 @@ __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, b
     if (nv > 0) { if (stream) __stcs(ptr, v0); else ptr[0] = v0; }
     if (nv > 1) { if (stream) __stcs(ptr + 1, v1); else ptr[1] = v1; }
   }
+}
+
+// how many row-chunks to split a plane into so that the grid fills the machine a few times over
+inline void pick_chunks(long long base_items, int rows_out, int min_rows, int* n_chunks, int* CH) {
+  const long long want = 148LL * 32 * 3;
+  int nc = 1;
+  if (base_items < want) {
+    nc = (int)((want + base_items - 1) / (base_items > 0 ? base_items : 1));
+    const int max_chunks = (rows_out + min_rows - 1) / min_rows;
+    if (nc > max_chunks) nc = max_chunks;
+    if (nc < 1) nc = 1;
+  }
+  int ch = (rows_out + nc - 1) / nc;
+  ch = (ch + min_rows - 1) / min_rows * min_rows;
+  *CH = ch;
+  *n_chunks = (rows_out + ch - 1) / ch;
+}
+
+inline bool aligned_plane(const void* base, long long ps, int pitch) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (pitch % 4 == 0) && (ps % 4 == 0);
 }
 
 // ================================================================================================
@@ -74,13 +217,12 @@ struct AfbCfg {
   static constexpr int OFF = HLA - (L - 2);          // lane window offset inside its aligned read
   static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
   static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
-  static constexpr int CPR = SW / 4;                 // 16-byte chunks per staged row
-  static constexpr int NCH = (2 * CPR + 31) / 32;    // chunks per lane per stage
   static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
-  static constexpr int NFIX = (4 * (HLA + L) + 31) / 32;  // border fix-ups per lane per stage (2 rows x 2 sides)
+  static constexpr int NFIX = (4 * (HLA + L) + 31) / 32;  // border fix-ups per lane per stage
   static constexpr int SMEM_BYTES = NS * 2 * SW * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
-  static constexpr int UNR = L / 2;                  // window period: stage copies in the unrolled loop
+  static constexpr int UNR = L / 2;                  // window period: stage copies in the dispatch
+  using Loader = StripLoader<2, SW, NS, NFIX>;
 };
 
 // one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
@@ -153,7 +295,7 @@ template <int L>
 __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
                                                    int CH) {
   using C = AfbCfg<L>;
-  extern __shared__ __align__(16) float ring[];  // this warp's staging ring: NS stages x 2 rows x SW floats
+  extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
   long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
   const int strip = (int)(item % n_strips);
@@ -165,91 +307,12 @@ __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbPa
   const int ky0 = chunk * CH;
   const int ky1 = imin(ky0 + CH, p.Ho);
   const int n_stage = (ky1 - ky0) + C::PRO;
-  const int c_a = 2 * k0 - C::HLA;
-  const int r_begin = 2 * ky0 - (L - 2);
   const int nvalid = imin(64, p.Wo - k0);
-  const int need_cols = C::HLA + 2 * nvalid;  // staged columns that feed a valid output
-  const int H = p.H, W = p.W, mode = p.mode, xpitch = p.xpitch;
-  const float* xp = p.x + (long long)plane * p.xps;
 
-  // ---- static per-lane schedule (computed once; only the source rows change from stage to stage) ----
-  // (a) border fix-ups: staged columns outside the image are filled from the staged copy of the column the
-  //     boundary extension maps them to (or with zeros) after the stage has landed -- two shared-memory
-  //     accesses instead of an element-wise global gather.  Possible when that source column is staged too.
-  const int nleft = imin(imax(0, -c_a), need_cols);
-  const int sr0 = imax(W - c_a, 0);                   // first staged column right of the image
-  const int nright = imax(0, need_cols - sr0);
-  const int nb_row = nleft + nright;
-  int fix_dst[C::NFIX], fix_src[C::NFIX];
-  bool bad = (2 * nb_row > 32 * C::NFIX);
-#pragma unroll
-  for (int q = 0; q < C::NFIX; ++q) {
-    fix_dst[q] = -1;
-    fix_src[q] = -1;
-    const int e = lane + 32 * q;
-    if (e < 2 * nb_row) {
-      const int rr = (e >= nb_row) ? 1 : 0;
-      const int idx = e - rr * nb_row;
-      const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
-      const int g = ext_index(c_a + sidx, W, mode);
-      fix_dst[q] = rr * C::SW + sidx;
-      if (g >= 0) {
-        const int ss = g - c_a;
-        if (ss < 0 || ss >= need_cols) bad = true;
-        fix_src[q] = rr * C::SW + ss;
-      }
-    }
-  }
-  const bool use_cold = __any_sync(0xffffffffu, bad);   // e.g. 'periodic': the source is in another strip
-  const bool any_fix = (nb_row > 0) && !use_cold;
-  // (b) copy schedule: kind 0 nothing, 1 aligned 16-byte cp.async, 2 element-wise (only when use_cold)
-  int c_soff[C::NCH], c_gcol[C::NCH], c_kind[C::NCH];
-#pragma unroll
-  for (int k = 0; k < C::NCH; ++k) {
-    const int ch = lane + 32 * k;
-    const int rr = (ch >= C::CPR) ? 1 : 0;
-    const int cc = ch - rr * C::CPR;
-    const int gc = c_a + 4 * cc;
-    c_soff[k] = rr * C::SW + 4 * cc;
-    c_gcol[k] = gc;
-    int kind = 0;
-    if (ch < 2 * C::CPR && 4 * cc < need_cols) {
-      const bool inside = (gc >= 0 && gc + 3 < W);
-      const bool partly = (gc + 3 >= 0 && gc < W);
-      // a chunk straddling the right edge may be read whole: the row pitch covers it (launcher guarantees)
-      if (inside || (partly && gc >= 0 && gc + 3 < xpitch && !use_cold)) kind = 1;
-      else if (use_cold) kind = 2;
-    }
-    c_kind[k] = kind | (rr << 2);
-  }
-
-  auto issue = [&](int t) {
-    if (t < n_stage) {
-      float* dst = ring + (t & (C::NS - 1)) * (2 * C::SW);
-      const int r0 = r_begin + 2 * t;
-      const int gr0 = ((unsigned)r0 < (unsigned)H) ? r0 : ext_index_cold(r0, H, mode);
-      const int gr1 = ((unsigned)(r0 + 1) < (unsigned)H) ? r0 + 1 : ext_index_cold(r0 + 1, H, mode);
-      const float* src0 = xp + (long long)gr0 * xpitch;
-      const float* src1 = xp + (long long)gr1 * xpitch;
-#pragma unroll
-      for (int k = 0; k < C::NCH; ++k) {
-        const int kind = c_kind[k] & 3;
-        if (kind != 0) {
-          const bool rr = (c_kind[k] & 4) != 0;
-          const int gr = rr ? gr1 : gr0;
-          const float* src = rr ? src1 : src0;
-          float* d = dst + c_soff[k];
-          if (gr < 0) *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-          else if (kind == 1) cp_async16(d, src + c_gcol[k]);
-          else load_chunk_cold(d, src, c_gcol[k], W, mode);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-
-#pragma unroll 1
-  for (int t = 0; t < C::NS - 1; ++t) issue(t);
+  typename C::Loader ld;
+  ld.init(ring, p.x + (long long)plane * p.xps, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA,
+          C::HLA + 2 * nvalid, 2 * ky0 - (L - 2), n_stage, lane);
+  ld.prologue();
 
   float wl[L][2], wh[L][2];
 #pragma unroll
@@ -264,16 +327,8 @@ __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbPa
   int uu = 0;
 #pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
-    cp_async_wait<C::NS - 2>();
-    __syncwarp();
-    float* stage = ring + (t & (C::NS - 1)) * (2 * C::SW);
-    if (any_fix) {
-#pragma unroll
-      for (int q = 0; q < C::NFIX; ++q)
-        if (fix_dst[q] >= 0) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
-      __syncwarp();
-    }
-    issue(t + C::NS - 1);
+    const float* stage = ld.acquire(t);
+    ld.issue(t + C::NS - 1);
     afb_stage_dispatch<L, 0>(uu, p, stage + 4 * lane, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
   }
@@ -284,22 +339,11 @@ template <int L>
 inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
   using C = AfbCfg<L>;
   // aligned 16-byte staging needs an aligned source; anything else takes the generic kernel
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && (p.xpitch % 4 == 0) && (p.xps % 4 == 0);
-  if (!vec_ok) return kNoFastPath;
+  if (!aligned_plane(p.x, p.xps, p.xpitch)) return kNoFastPath;
   const int n_strips = (p.Wo + 63) / 64;
-  // enough independent warps to fill the machine several times over; otherwise split the rows
-  const long long want = 148LL * 32 * 3;
-  const long long base = (long long)p.planes * n_strips;
-  int n_chunks = 1;
-  if (base < want) {
-    n_chunks = (int)((want + base - 1) / (base > 0 ? base : 1));
-    const int max_chunks = (p.Ho + 15) / 16;
-    if (n_chunks > max_chunks) n_chunks = max_chunks;
-    if (n_chunks < 1) n_chunks = 1;
-  }
-  const int CH = (p.Ho + n_chunks - 1) / n_chunks;
-  n_chunks = (p.Ho + CH - 1) / CH;
-  const long long blocks = base * n_chunks;
+  int n_chunks, CH;
+  pick_chunks((long long)p.planes * n_strips, p.Ho, 16, &n_chunks, &CH);
+  const long long blocks = (long long)p.planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
   afb2d_stream<L><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
@@ -322,8 +366,7 @@ inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
   }
 }
 
-inline int try_launch_fwd_j1(const DtParams&, cudaStream_t) { return kNoFastPath; }
-inline int try_launch_fwd_j2plus(const DtParams&, cudaStream_t) { return kNoFastPath; }
+#include "fast_dtcwt.cuh"
 
 }  // namespace fast
 }  // namespace b200w
