@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtPa
   const int ncols = imin(64, p.W - c0);
 
   typename C::Loader ld;
-  ld.init(ring, p.in + (long long)plane * p.inps, p.H, p.W, p.inpitch, p.sym ? B200W_MODE_SYMMETRIC : B200W_MODE_ZERO,
+  ld.init(ring, p.in + (long long)plane * p.inps, p.inps, 1, p.H, p.W, p.inpitch,
+          p.sym ? B200W_MODE_SYMMETRIC : B200W_MODE_ZERO,
           c0 - C::HLA, C::HLA + ncols + C::M, 2 * qy0 - C::M, n_stage, lane);
   ld.prologue();
 
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(32) fwd_j2plus_stream(const __grid_constant__ 
   const int nq = imin(32, Q - q0);
 
   typename C::Loader ld;
-  ld.init(ring, p.in + (long long)plane * p.inps, p.H, p.W, p.inpitch, B200W_MODE_SYMMETRIC, 4 * q0 - C::HLA,
+  ld.init(ring, p.in + (long long)plane * p.inps, p.inps, 1, p.H, p.W, p.inpitch, B200W_MODE_SYMMETRIC, 4 * q0 - C::HLA,
           C::HLA + 4 * nq + C::HL, 4 * qy0 + 2 - MQ, n_stage, lane);
   ld.prologue();
 

@@ -45,29 +45,31 @@ __device__ __noinline__ int ext_index_cold(int i, int N, int mode) { return ext_
 // General (rare) stage load: rows outside the image (remapped or zero-filled) and, when `elementwise`,
 // border columns gathered element by element.  Used for the few stages that touch the top/bottom border
 // and for extension modes whose source column is not inside the strip (e.g. 'periodic').
-__device__ __noinline__ void load_stage_general(float* dst, int rows, int sw, int cpr, const float* plane, int r0,
-                                                int H, int W, int pitch, int mode, int c_a, int need_cols,
-                                                int elementwise, int lane) {
+__device__ __noinline__ void load_stage_general(float* dst, int rows, int rpp, int sw, int cpr, const float* plane,
+                                                long long ps, int nplanes, int r0, int H, int W, int pitch, int mode,
+                                                int c_a, int need_cols, int elementwise, int lane) {
   for (int ch = lane; ch < rows * cpr; ch += 32) {
-    const int rr = ch / cpr;
-    const int cc = ch - rr * cpr;
-    if (4 * cc >= need_cols) continue;
+    const int v = ch / cpr;
+    const int cc = ch - v * cpr;
+    const int g = v / rpp;
+    const int rr = v - g * rpp;
+    if (4 * cc >= need_cols || g >= nplanes) continue;
     const int gr = ext_index(r0 + rr, H, mode);
-    float* d = dst + rr * sw + 4 * cc;
+    float* d = dst + v * sw + 4 * cc;
     const int gc = c_a + 4 * cc;
     if (gr < 0) {
       *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
-    const float* src = plane + (long long)gr * pitch;
+    const float* src = plane + (long long)g * ps + (long long)gr * pitch;
     const bool inside = (gc >= 0 && gc + 3 < W);
     if (inside || (!elementwise && gc >= 0 && gc < W && gc + 3 < pitch)) {
       cp_async16(d, src + gc);
     } else if (elementwise) {
       for (int e = 0; e < 4; ++e) {
-        const int g = ext_index(gc + e, W, mode);
-        if (g < 0) d[e] = 0.f;
-        else cp_async4(d + e, src + g);
+        const int gg = ext_index(gc + e, W, mode);
+        if (gg < 0) d[e] = 0.f;
+        else cp_async4(d + e, src + gg);
       }
     }
   }
@@ -81,45 +83,50 @@ __device__ __noinline__ void load_stage_general(float* dst, int rows, int sw, in
 //   - rows outside the image / exotic modes go through load_stage_general (out of line).
 // The caller guarantees: plane base 16-byte aligned, pitch % 4 == 0, c_a % 4 == 0, SW % 4 == 0.
 // ================================================================================================
-template <int ROWS, int SW, int NS, int NFIX>
+template <int ROWS, int SW, int NS, int NFIX, int RPP = ROWS>
 struct StripLoader {
+  // ROWS "virtual" rows per stage = (ROWS / RPP) planes x RPP image rows: a warp working on a narrow
+  // remainder strip stages the same rows of several planes at once (lanes are split between planes).
   static constexpr int CPR = SW / 4;
   static constexpr int NCH = (ROWS * CPR + 31) / 32;
   static constexpr int STAGE = ROWS * SW;  // floats per stage
 
   float* ring;
   const float* plane;
-  int H, W, pitch, mode, c_a, need_cols, r_begin, n_stage, lane;
+  long long ps;
+  int nplanes, H, W, pitch, mode, c_a, need_cols, r_begin, n_stage, lane;
   bool use_cold, any_fix;
   int c_soff[NCH];
   long long c_goff[NCH];
   bool c_on[NCH];
   int fix_dst[NFIX], fix_src[NFIX];
 
-  __device__ __forceinline__ void init(float* ring_, const float* plane_, int H_, int W_, int pitch_, int mode_,
-                                       int c_a_, int need_cols_, int r_begin_, int n_stage_, int lane_) {
-    ring = ring_; plane = plane_; H = H_; W = W_; pitch = pitch_; mode = mode_; c_a = c_a_;
-    need_cols = need_cols_; r_begin = r_begin_; n_stage = n_stage_; lane = lane_;
+  __device__ __forceinline__ void init(float* ring_, const float* plane_, long long ps_, int nplanes_, int H_, int W_,
+                                       int pitch_, int mode_, int c_a_, int need_cols_, int r_begin_, int n_stage_,
+                                       int lane_) {
+    ring = ring_; plane = plane_; ps = ps_; nplanes = nplanes_; H = H_; W = W_; pitch = pitch_; mode = mode_;
+    c_a = c_a_; need_cols = need_cols_; r_begin = r_begin_; n_stage = n_stage_; lane = lane_;
     const int nleft = imin(imax(0, -c_a), need_cols);
     const int sr0 = imax(W - c_a, 0);  // first staged column right of the image
     const int nright = imax(0, need_cols - sr0);
     const int nb_row = nleft + nright;
-    bool bad = (ROWS * nb_row > 32 * NFIX);
+    const int vrows = nplanes * RPP;
+    bool bad = (vrows * nb_row > 32 * NFIX);
 #pragma unroll
     for (int q = 0; q < NFIX; ++q) {
       fix_dst[q] = -1;
       fix_src[q] = -1;
       const int e = lane + 32 * q;
-      if (e < ROWS * nb_row) {
-        const int rr = e / (nb_row > 0 ? nb_row : 1);
-        const int idx = e - rr * nb_row;
+      if (e < vrows * nb_row) {
+        const int v = e / (nb_row > 0 ? nb_row : 1);
+        const int idx = e - v * nb_row;
         const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
         const int g = ext_index(c_a + sidx, W, mode);
-        fix_dst[q] = rr * SW + sidx;
+        fix_dst[q] = v * SW + sidx;
         if (g >= 0) {
           const int ss = g - c_a;
           if (ss < 0 || ss >= need_cols) bad = true;
-          fix_src[q] = rr * SW + ss;
+          fix_src[q] = v * SW + ss;
         }
       }
     }
@@ -128,27 +135,31 @@ struct StripLoader {
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int ch = lane + 32 * k;
-      const int rr = ch / CPR;
-      const int cc = ch - rr * CPR;
+      const int v = ch / CPR;
+      const int cc = ch - v * CPR;
+      const int g = v / RPP;
+      const int rr = v - g * RPP;
       const int gc = c_a + 4 * cc;
-      c_soff[k] = rr * SW + 4 * cc;
-      c_goff[k] = (long long)rr * pitch + gc;
+      c_soff[k] = v * SW + 4 * cc;
+      c_goff[k] = (long long)g * ps + (long long)rr * pitch + gc;
       // a chunk straddling the right edge is read whole: the row pitch covers it
-      c_on[k] = (ch < ROWS * CPR) && (4 * cc < need_cols) && (gc >= 0) && (gc < W) && (gc + 3 < pitch);
+      c_on[k] = (ch < ROWS * CPR) && (g < nplanes) && (4 * cc < need_cols) && (gc >= 0) && (gc < W) &&
+                (gc + 3 < pitch);
     }
   }
 
   __device__ __forceinline__ void issue(int t) {
     if (t < n_stage) {
       float* dst = ring + (t % NS) * STAGE;
-      const int r0 = r_begin + ROWS * t;
-      if (!use_cold && r0 >= 0 && r0 + ROWS <= H) {
+      const int r0 = r_begin + RPP * t;
+      if (!use_cold && r0 >= 0 && r0 + RPP <= H) {
         const float* src = plane + (long long)r0 * pitch;
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
           if (c_on[k]) cp_async16(dst + c_soff[k], src + c_goff[k]);
       } else {
-        load_stage_general(dst, ROWS, SW, CPR, plane, r0, H, W, pitch, mode, c_a, need_cols, use_cold ? 1 : 0, lane);
+        load_stage_general(dst, ROWS, RPP, SW, CPR, plane, ps, nplanes, r0, H, W, pitch, mode, c_a, need_cols,
+                           use_cold ? 1 : 0, lane);
       }
     }
     cp_async_commit();
@@ -210,29 +221,33 @@ inline bool aligned_plane(const void* base, long long ps, int pitch) {
 //   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
 //   stage = 2 input rows = 1 output row.
 // ================================================================================================
-template <int L>
+template <int L, int PW = 32>
 struct AfbCfg {
+  // PW = column pairs per plane handled by one warp: 32 -> the warp owns one 64-column strip of one plane;
+  // PW < 32 -> a narrow remainder strip, the warp's lanes are split over G = 32/PW planes.
+  static constexpr int G = 32 / PW;
   static constexpr int HLA = ((L - 2) + 3) / 4 * 4;  // left halo rounded up to 16 bytes
-  static constexpr int SW = HLA + 128;               // staged floats per row
+  static constexpr int SW = HLA + 4 * PW;            // staged floats per row (per plane)
   static constexpr int OFF = HLA - (L - 2);          // lane window offset inside its aligned read
   static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
   static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
   static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
-  static constexpr int NFIX = (4 * (HLA + L) + 31) / 32;  // border fix-ups per lane per stage
-  static constexpr int SMEM_BYTES = NS * 2 * SW * 4;
+  static constexpr int NFIX = (PW == 32) ? (4 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage
+  static constexpr int SMEM_BYTES = NS * 2 * G * SW * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
   static constexpr int UNR = L / 2;                  // window period: stage copies in the dispatch
-  using Loader = StripLoader<2, SW, NS, NFIX>;
+  using Loader = StripLoader<2 * G, SW, NS, NFIX, 2>;
+  static_assert(4 * NV - 4 <= HLA || PW == 32, "lane window must stay inside its plane's staged segment");
 };
 
 // one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
 // the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
 // window period, so every window index is a compile-time constant: the window never moves.
-template <int L, int U>
+template <int L, int PW, int U>
 __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
                                           bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
                                           int Wo, int nv) {
-  using C = AfbCfg<L>;
+  using C = AfbCfg<L, PW>;
   float xa[4 * C::NV], xb[4 * C::NV];
 #pragma unroll
   for (int q = 0; q < C::NV; ++q) {
@@ -281,36 +296,42 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
   }
 }
 
-template <int L, int U>
+template <int L, int PW, int U>
 __device__ __forceinline__ void afb_stage_dispatch(int uu, const AfbParams& p, const float* s0, float (&wl)[L][2],
                                                    float (&wh)[L][2], bool emit, float*& ll_ptr, float*& hi_ptr,
                                                    long long band, int llpitch, int Wo, int nv) {
-  if constexpr (U < AfbCfg<L>::UNR) {
-    if (uu == U) afb_stage<L, U>(p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-    else afb_stage_dispatch<L, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+  if constexpr (U < AfbCfg<L, PW>::UNR) {
+    if (uu == U) afb_stage<L, PW, U>(p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    else afb_stage_dispatch<L, PW, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
   }
 }
 
-template <int L>
+// strip0 / n_strips: the 64-column strips this launch covers (PW == 32), or the single remainder strip
+// starting at output column k_rem (PW < 32, n_strips == 1).
+template <int L, int PW>
 __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
-                                                   int CH) {
-  using C = AfbCfg<L>;
+                                                   int CH, int k_rem) {
+  using C = AfbCfg<L, PW>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
   long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
   const int strip = (int)(item % n_strips);
   item /= n_strips;
   const int chunk = (int)(item % n_chunks);
-  const int plane = (int)(item / n_chunks);
+  const int pgroup = (int)(item / n_chunks);
+  const int g = lane / PW, jp = lane % PW;        // plane within the group, column pair within the plane
+  const int plane0 = pgroup * C::G;
+  const int nplanes = imin(C::G, p.planes - plane0);
+  const int plane = plane0 + g;
 
-  const int k0 = strip * 64;
+  const int k0 = (PW == 32) ? strip * 64 : k_rem;
   const int ky0 = chunk * CH;
   const int ky1 = imin(ky0 + CH, p.Ho);
   const int n_stage = (ky1 - ky0) + C::PRO;
-  const int nvalid = imin(64, p.Wo - k0);
+  const int nvalid = imin(2 * PW, p.Wo - k0);
 
   typename C::Loader ld;
-  ld.init(ring, p.x + (long long)plane * p.xps, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA,
+  ld.init(ring, p.x + (long long)plane0 * p.xps, p.xps, nplanes, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA,
           C::HLA + 2 * nvalid, 2 * ky0 - (L - 2), n_stage, lane);
   ld.prologue();
 
@@ -319,35 +340,55 @@ __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbPa
   for (int j = 0; j < L; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
 
   const long long band = (long long)p.Ho * p.Wo;
-  float* ll_ptr = p.ll + (long long)plane * p.llps + (long long)ky0 * p.llpitch + k0 + 2 * lane;
-  float* hi_ptr = p.highs + (long long)plane * 3 * band + (long long)ky0 * p.Wo + k0 + 2 * lane;
-  const int nv = imax(0, imin(2, p.Wo - (k0 + 2 * lane)));
+  float* ll_ptr = p.ll + (long long)plane * p.llps + (long long)ky0 * p.llpitch + k0 + 2 * jp;
+  float* hi_ptr = p.highs + (long long)plane * 3 * band + (long long)ky0 * p.Wo + k0 + 2 * jp;
+  const int nv = (g < nplanes) ? imax(0, imin(2, p.Wo - (k0 + 2 * jp))) : 0;
   const int llpitch = p.llpitch, Wo = p.Wo;
+  const int lane_off = g * (2 * C::SW) + 4 * jp;
 
   int uu = 0;
 #pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    afb_stage_dispatch<L, 0>(uu, p, stage + 4 * lane, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    afb_stage_dispatch<L, PW, 0>(uu, p, stage + lane_off, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
   }
   cp_async_wait<0>();
 }
 
+template <int L, int PW>
+inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips, int k_rem) {
+  using C = AfbCfg<L, PW>;
+  const long long groups = ((long long)p.planes + C::G - 1) / C::G;
+  int n_chunks, CH;
+  pick_chunks(groups * n_strips, p.Ho, 16, &n_chunks, &CH);
+  const long long blocks = groups * n_strips * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return B200W_ESIZE;
+  afb2d_stream<L, PW><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+  return 0;
+}
+
 template <int L>
 inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
-  using C = AfbCfg<L>;
   // aligned 16-byte staging needs an aligned source; anything else takes the generic kernel
   if (!aligned_plane(p.x, p.xps, p.xpitch)) return kNoFastPath;
-  const int n_strips = (p.Wo + 63) / 64;
-  int n_chunks, CH;
-  pick_chunks((long long)p.planes * n_strips, p.Ho, 16, &n_chunks, &CH);
-  const long long blocks = (long long)p.planes * n_strips * n_chunks;
-  if (blocks <= 0) return 0;
-  if (blocks > 2147483647LL) return kNoFastPath;
-  afb2d_stream<L><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
-  return 0;
+  // full 64-column strips, plus one narrow remainder strip whose warps are shared between planes
+  int n_full = p.Wo / 64;
+  const int rem = p.Wo - 64 * n_full;
+  const int pairs = (rem + 1) / 2;
+  int pw = 0;
+  if (rem > 0) {
+    if (pairs <= 4) pw = 4;
+    else if (pairs <= 16) pw = 16;
+    else n_full += 1;  // wide remainder: an ordinary strip
+  }
+  int rc = 0;
+  if (n_full > 0) rc = launch_afb_part<L, 32>(p, stream, n_full, 0);
+  if (rc == 0 && pw == 4) rc = launch_afb_part<L, 4>(p, stream, 1, p.Wo - rem);
+  if (rc == 0 && pw == 16) rc = launch_afb_part<L, 16>(p, stream, 1, p.Wo - rem);
+  return rc;
 }
 
 inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
