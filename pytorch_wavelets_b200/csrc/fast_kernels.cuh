@@ -374,21 +374,12 @@ template <int L>
 inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
   // aligned 16-byte staging needs an aligned source; anything else takes the generic kernel
   if (!aligned_plane(p.x, p.xps, p.xpitch)) return kNoFastPath;
-  // full 64-column strips, plus one narrow remainder strip whose warps are shared between planes
-  int n_full = p.Wo / 64;
-  const int rem = p.Wo - 64 * n_full;
-  const int pairs = (rem + 1) / 2;
-  int pw = 0;
-  if (rem > 0) {
-    if (pairs <= 4) pw = 4;
-    else if (pairs <= 16) pw = 16;
-    else n_full += 1;  // wide remainder: an ordinary strip
-  }
-  int rc = 0;
-  if (n_full > 0) rc = launch_afb_part<L, 32>(p, stream, n_full, 0);
-  if (rc == 0 && pw == 4) rc = launch_afb_part<L, 4>(p, stream, 1, p.Wo - rem);
-  if (rc == 0 && pw == 16) rc = launch_afb_part<L, 16>(p, stream, 1, p.Wo - rem);
-  return rc;
+  // Every 64-column strip (including a narrow last one) is an ordinary warp item.  Measured on B200: the
+  // kernel is latency/occupancy-bound, not issue-bound, so a mostly-idle last strip costs almost nothing,
+  // while packing it across planes (AfbCfg<L, PW<32>, kept for reference) needs a second launch that is
+  // slower than what it saves (profiles/r01_notes.md).
+  const int n_strips = (p.Wo + 63) / 64;
+  return launch_afb_part<L, 32>(p, stream, n_strips, 0);
 }
 
 inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
