@@ -23,6 +23,8 @@ namespace fast {
 
 constexpr int kNoFastPath = 1;
 static int g_force_generic = 0;
+static int g_tune_minb = 0;
+static int g_tune_hs = 0;
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -96,9 +98,8 @@ struct StripLoader {
   long long ps;
   int nplanes, H, W, pitch, mode, c_a, need_cols, r_begin, n_stage, lane;
   bool use_cold, any_fix;
-  int c_soff[NCH];
-  long long c_goff[NCH];
-  bool c_on[NCH];
+  int c_soff[NCH];  // staged offset of the chunk this lane copies (-1: none)
+  int c_goff[NCH];  // its source offset from the stage's first row (plane stride and pitch folded in when G == 1)
   int fix_dst[NFIX], fix_src[NFIX];
 
   __device__ __forceinline__ void init(float* ring_, const float* plane_, long long ps_, int nplanes_, int H_, int W_,
@@ -140,11 +141,11 @@ struct StripLoader {
       const int g = v / RPP;
       const int rr = v - g * RPP;
       const int gc = c_a + 4 * cc;
-      c_soff[k] = v * SW + 4 * cc;
-      c_goff[k] = (long long)g * ps + (long long)rr * pitch + gc;
       // a chunk straddling the right edge is read whole: the row pitch covers it
-      c_on[k] = (ch < ROWS * CPR) && (g < nplanes) && (4 * cc < need_cols) && (gc >= 0) && (gc < W) &&
-                (gc + 3 < pitch);
+      const bool on = (ch < ROWS * CPR) && (g < nplanes) && (4 * cc < need_cols) && (gc >= 0) && (gc < W) &&
+                      (gc + 3 < pitch);
+      c_soff[k] = on ? (v * SW + 4 * cc) : -1;
+      c_goff[k] = (int)((long long)g * ps + (long long)rr * pitch + gc);  // launcher keeps this below 2^31
     }
   }
 
@@ -156,7 +157,7 @@ struct StripLoader {
         const float* src = plane + (long long)r0 * pitch;
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
-          if (c_on[k]) cp_async16(dst + c_soff[k], src + c_goff[k]);
+          if (c_soff[k] >= 0) cp_async16(dst + c_soff[k], src + c_goff[k]);
       } else {
         load_stage_general(dst, ROWS, RPP, SW, CPR, plane, ps, nplanes, r0, H, W, pitch, mode, c_a, need_cols,
                            use_cold ? 1 : 0, lane);
@@ -221,7 +222,7 @@ inline bool aligned_plane(const void* base, long long ps, int pitch) {
 //   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
 //   stage = 2 input rows = 1 output row.
 // ================================================================================================
-template <int L, int PW = 32>
+template <int L, int PW = 32, int HSM = 2>
 struct AfbCfg {
   // PW = column pairs per plane handled by one warp: 32 -> the warp owns one 64-column strip of one plane;
   // PW < 32 -> a narrow remainder strip, the warp's lanes are split over G = 32/PW planes.
@@ -231,23 +232,28 @@ struct AfbCfg {
   static constexpr int OFF = HLA - (L - 2);          // lane window offset inside its aligned read
   static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
   static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
-  static constexpr int NS = 4;                       // ring depth (stages of 2 rows)
-  static constexpr int NFIX = (PW == 32) ? (4 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage
-  static constexpr int SMEM_BYTES = NS * 2 * G * SW * 4;
-  static constexpr int PRO = (L - 2) / 2;            // prologue stages before the first output row
-  static constexpr int UNR = L / 2;                  // window period: stage copies in the dispatch
-  using Loader = StripLoader<2 * G, SW, NS, NFIX, 2>;
+  // half-stages (2 input rows = 1 output row) per stage: the largest of 4, 2, 1 dividing the window period
+  static constexpr int HS0 = ((L / 2) % 4 == 0) ? 4 : (((L / 2) % 2 == 0) ? 2 : 1);
+  static constexpr int HS = (HS0 < HSM) ? HS0 : HSM;
+  static constexpr int RPS = 2 * HS;                 // image rows per stage
+  static constexpr int NS = (HS == 4) ? 2 : ((HS == 2) ? 3 : 4);  // ring depth in stages
+  static constexpr int NFIX = (PW == 32) ? (RPS * 2 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage
+  static constexpr int SMEM_BYTES = NS * RPS * G * SW * 4;
+  static constexpr int PRO = (L - 2) / 2;            // prologue half-stages before the first output row
+  static constexpr int UNR = L / 2;                  // window period in half-stages
+  static constexpr int UNS = UNR / HS;               // ... in stages: copies of the stage body
+  using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS>;
   static_assert(4 * NV - 4 <= HLA || PW == 32, "lane window must stay inside its plane's staged segment");
 };
 
 // one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
 // the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
 // window period, so every window index is a compile-time constant: the window never moves.
-template <int L, int PW, int U>
+template <int L, int PW, int HSM, int U>
 __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
                                           bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
                                           int Wo, int nv) {
-  using C = AfbCfg<L, PW>;
+  using C = AfbCfg<L, PW, HSM>;
   float xa[4 * C::NV], xb[4 * C::NV];
 #pragma unroll
   for (int q = 0; q < C::NV; ++q) {
@@ -296,22 +302,36 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
   }
 }
 
-template <int L, int PW, int U>
-__device__ __forceinline__ void afb_stage_dispatch(int uu, const AfbParams& p, const float* s0, float (&wl)[L][2],
-                                                   float (&wh)[L][2], bool emit, float*& ll_ptr, float*& hi_ptr,
-                                                   long long band, int llpitch, int Wo, int nv) {
-  if constexpr (U < AfbCfg<L, PW>::UNR) {
-    if (uu == U) afb_stage<L, PW, U>(p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-    else afb_stage_dispatch<L, PW, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+template <int L, int PW, int HSM, int V>
+__device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, const float* s0, float (&wl)[L][2],
+                                                   float (&wh)[L][2], int h0, int h_emit_end, float*& ll_ptr,
+                                                   float*& hi_ptr, long long band, int llpitch, int Wo, int nv) {
+  using C = AfbCfg<L, PW, HSM>;
+  if constexpr (V < C::UNS) {
+    if (vv == V) {
+      // h0 = index of this stage's first half-stage; output rows are emitted for PRO <= h < h_emit_end
+      afb_stage<L, PW, HSM, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      if constexpr (C::HS >= 2)
+        afb_stage<L, PW, HSM, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
+                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      if constexpr (C::HS == 4) {
+        afb_stage<L, PW, HSM, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
+                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+        afb_stage<L, PW, HSM, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
+                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      }
+    } else {
+      afb_stage_dispatch<L, PW, HSM, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+    }
   }
 }
 
 // strip0 / n_strips: the 64-column strips this launch covers (PW == 32), or the single remainder strip
 // starting at output column k_rem (PW < 32, n_strips == 1).
-template <int L, int PW>
-__global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
+template <int L, int PW, int MINB, int HSM>
+__global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
                                                    int CH, int k_rem) {
-  using C = AfbCfg<L, PW>;
+  using C = AfbCfg<L, PW, HSM>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
   long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
@@ -327,7 +347,8 @@ __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbPa
   const int k0 = (PW == 32) ? strip * 64 : k_rem;
   const int ky0 = chunk * CH;
   const int ky1 = imin(ky0 + CH, p.Ho);
-  const int n_stage = (ky1 - ky0) + C::PRO;
+  const int n_half = (ky1 - ky0) + C::PRO;             // half-stages: PRO of warm-up, then one output row each
+  const int n_stage = (n_half + C::HS - 1) / C::HS;
   const int nvalid = imin(2 * PW, p.Wo - k0);
 
   typename C::Loader ld;
@@ -344,29 +365,43 @@ __global__ void __launch_bounds__(32) afb2d_stream(const __grid_constant__ AfbPa
   float* hi_ptr = p.highs + (long long)plane * 3 * band + (long long)ky0 * p.Wo + k0 + 2 * jp;
   const int nv = (g < nplanes) ? imax(0, imin(2, p.Wo - (k0 + 2 * jp))) : 0;
   const int llpitch = p.llpitch, Wo = p.Wo;
-  const int lane_off = g * (2 * C::SW) + 4 * jp;
+  const int lane_off = g * (C::RPS * C::SW) + 4 * jp;
 
-  int uu = 0;
+  int vv = 0;
 #pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    afb_stage_dispatch<L, PW, 0>(uu, p, stage + lane_off, wl, wh, t >= C::PRO, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+    afb_stage_dispatch<L, PW, HSM, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
+                                 nv);
+    vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }
   cp_async_wait<0>();
 }
 
+template <int L, int PW, int MINB, int HSM>
+inline void launch_afb_kernel(const AfbParams& p, cudaStream_t stream, long long blocks, int n_strips, int n_chunks,
+                              int CH, int k_rem) {
+  using C = AfbCfg<L, PW, HSM>;
+  afb2d_stream<L, PW, MINB, HSM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+}
+
 template <int L, int PW>
 inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips, int k_rem) {
-  using C = AfbCfg<L, PW>;
-  const long long groups = ((long long)p.planes + C::G - 1) / C::G;
+  constexpr int G = 32 / PW;
+  const long long groups = ((long long)p.planes + G - 1) / G;
   int n_chunks, CH;
   pick_chunks(groups * n_strips, p.Ho, 16, &n_chunks, &CH);
   const long long blocks = groups * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return B200W_ESIZE;
-  afb2d_stream<L, PW><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+  // tuning knobs (experiments): register cap MINB and rows per stage (HSM half-stages)
+  if (g_tune_hs == 4) {
+    if (g_tune_minb == 24) launch_afb_kernel<L, PW, 24, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    else launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+  } else {
+    launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+  }
   return 0;
 }
 
