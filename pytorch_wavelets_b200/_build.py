@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libb200wave.so')
 SOURCES = ['b200wave.cu']
-HEADERS = ['common.h', 'tile_kernels.h', 'launch_params.h', 'fast_kernels.cuh', 'fast_dtcwt.cuh', os.path.join('..', '..', 'include', 'b200wave.h')]
+HEADERS = ['common.h', 'tile_kernels.h', 'launch_params.h', 'fast_kernels.cuh', 'fast_dtcwt.cuh', 'fast_inverse.cuh', os.path.join('..', '..', 'include', 'b200wave.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

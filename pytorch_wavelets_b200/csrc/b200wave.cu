@@ -104,6 +104,8 @@ int b200w_dwt_sfb2d(const float* ll, long long ll_plane_stride, int ll_pitch, co
   int rc = build_sfb(p, ll, ll_plane_stride, ll_pitch, highs, y, y_plane_stride, y_pitch, planes, Hc, Wc, Ho, Wo,
                      gh_lo, gh_hi, Lh, gw_lo, gw_hi, Lw, mode);
   if (rc) return rc;
+  rc = fast::try_launch_sfb(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
   return launch_tile(k_sfb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, sfb_smem_floats(Lh, Lw), stream);
 }
 

@@ -434,6 +434,7 @@ inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
 }
 
 #include "fast_dtcwt.cuh"
+#include "fast_inverse.cuh"
 
 }  // namespace fast
 }  // namespace b200w

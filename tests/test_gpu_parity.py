@@ -130,7 +130,8 @@ def test_dwt_vs_oracle(mode, wave, J, shape):
         assert np.array_equal(_n(yh[j]), oyh[j]), util.rel_err(_n(yh[j]), oyh[j])
     oy = orc.dwt_inverse(oyl, oyh, gf, mode)
     y = i((yl, yh))
-    assert np.array_equal(_n(y), oy), util.rel_err(_n(y), oy)
+    # synthesis: the streaming kernel runs the W pass before the H pass (they commute; fp32 rounding differs)
+    util.assert_close(_n(y), oy, TOL, 'inverse')
     # perfect reconstruction on the original extent
     H, W = shape[2:]
     assert np.abs(_n(y)[:, :, :H, :W] - x.numpy()).max() < 2e-5
@@ -434,8 +435,12 @@ def test_generic_and_auto_paths_agree():
     try:
         lib.b200w_debug_force_generic(1)
         a, b = f(x), d(x)
+        inv = pw.DWTInverse(wave='db4', mode='symmetric').to(DEV)
+        ya = inv(a)
     finally:
         lib.b200w_debug_force_generic(0)
     a2, b2 = f(x), d(x)
     assert torch.equal(a[0], a2[0]) and all(torch.equal(p, q) for p, q in zip(a[1], a2[1]))
     assert torch.equal(b[0], b2[0]) and all(torch.equal(p, q) for p, q in zip(b[1], b2[1]))
+    ya2 = inv(a2)
+    assert (ya - ya2).abs().max().item() <= 1e-5 * ya.abs().max().item()
