@@ -141,6 +141,8 @@ int b200w_dtcwt_inv_j1(const float* ll, long long ll_plane_stride, int ll_pitch,
   int rc = build_inv_j1(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0, L0,
                         g1, L1, mode);
   if (rc) return rc;
+  rc = fast::try_launch_inv_j1(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
   return launch_tile(k_inv_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj1_smem_floats(L0, L1), stream);
 }
 

@@ -223,3 +223,312 @@ inline int try_launch_sfb(const SfbParams& p, cudaStream_t stream) {
     default: return kNoFastPath;
   }
 }
+
+// ================================================================================================
+// K5 fast: DTCWT level-1 inverse (reference INV_J1.forward / inv_j1, transform_funcs.py:152-184).
+//   y = R1(C1(hh) + C0(hl)) + R0(C1(lh) + C0(ll)),  C/R = col/row filter with g0 (L0 taps) / g1 (L1 taps).
+// The passes commute, so the kernel runs the W pass on staged rows first and the H pass in a register
+// window:  A = R1(hh) + R0(lh),  B = R1(hl) + R0(ll),  y = C1(A) + C0(B).
+//   lane  = one complex column q (output columns 2q, 2q+1); strip = 32 complex columns;
+//   stage = one complex row i (quad rows 2i, 2i+1): the six orientation rows + two ll rows are staged with
+//           16-byte cp.async, c2q'd once per complex sample into three real band rows in shared memory
+//           (symmetric extension = copy of the mirrored band sample, row extension = mirrored complex row with
+//           the row parity swapped), then filtered.
+// Requires the default band-pass layout along the row (re/im adjacent, columns contiguous) and 16-byte
+// aligned rows; everything else takes the generic kernel.
+// ================================================================================================
+template <int L0, int L1>
+struct I1Cfg {
+  static constexpr int M0 = L0 / 2, M1 = L1 / 2, M = (M0 > M1) ? M0 : M1;
+  static constexpr int HLA = (M + 3) / 4 * 4;
+  static constexpr int SW = HLA + 64 + HLA;
+  static constexpr int CPR = SW / 4;
+  static constexpr int OFFX = HLA - M;
+  static constexpr int NX = OFFX + 2 * M + 2;
+  static constexpr int NV2 = (NX + 1) / 2;
+  static constexpr int MS = (M + 1) / 2;             // complex rows of context above / below
+  static constexpr int WR = 4 * MS + 2;              // quad rows held in the register window
+  static constexpr int UNR = WR / 2;                 // window period in stages
+  static constexpr int PRO = 2 * MS;
+  static constexpr int NS = 3;
+  static constexpr int VR = 8;                       // staged rows per stage: 6 orientations + 2 ll rows
+  static constexpr int STAGE = VR * SW;
+  static constexpr int BAND = 6 * SW;                // c2q'd band rows: (lh, hl, hh) x 2 quad rows
+  static constexpr int NCH = (VR * CPR + 31) / 32;
+  static constexpr int NHALO = HLA / 2;              // halo complex columns per side
+  static constexpr int NFIX = (8 * 2 * HLA + 31) / 32;  // border fix-ups: 8 real rows x 2 sides x HLA cols
+  static constexpr int SMEM_BYTES = (NS * STAGE + BAND) * 4;
+};
+
+template <int L0, int L1, int U>
+__device__ __forceinline__ void i1_stage(const DtParams& p, const float* band, const float* llrow, bool has_hi,
+                                         bool has_ll, float (&wA)[I1Cfg<L0, L1>::WR][2],
+                                         float (&wB)[I1Cfg<L0, L1>::WR][2], bool emit, float*& y_ptr, bool colvalid) {
+  using C = I1Cfg<L0, L1>;
+  constexpr int WR = C::WR;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    float xlh[2 * C::NV2], xhl[2 * C::NV2], xhh[2 * C::NV2], xll[2 * C::NV2];
+#pragma unroll
+    for (int q = 0; q < C::NV2; ++q) {
+      const float2 a = *reinterpret_cast<const float2*>(band + (0 * 2 + rr) * C::SW + 2 * q);
+      const float2 b = *reinterpret_cast<const float2*>(band + (1 * 2 + rr) * C::SW + 2 * q);
+      const float2 c = *reinterpret_cast<const float2*>(band + (2 * 2 + rr) * C::SW + 2 * q);
+      const float2 d = *reinterpret_cast<const float2*>(llrow + rr * C::SW + 2 * q);
+      xlh[2 * q] = a.x; xlh[2 * q + 1] = a.y;
+      xhl[2 * q] = b.x; xhl[2 * q + 1] = b.y;
+      xhh[2 * q] = c.x; xhh[2 * q + 1] = c.y;
+      xll[2 * q] = d.x; xll[2 * q + 1] = d.y;
+    }
+    const int S = (2 * U + rr) % WR;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float r1hh = 0.f, r1hl = 0.f, r0lh = 0.f, r0ll = 0.f;
+#pragma unroll
+      for (int j = 0; j < L1; ++j) {
+        const int ix = C::OFFX + e + (C::M - C::M1) + j;
+        r1hh = fmaf(p.f1.t[j], xhh[ix], r1hh);
+        r1hl = fmaf(p.f1.t[j], xhl[ix], r1hl);
+      }
+#pragma unroll
+      for (int j = 0; j < L0; ++j) {
+        const int ix = C::OFFX + e + (C::M - C::M0) + j;
+        r0lh = fmaf(p.f0.t[j], xlh[ix], r0lh);
+        r0ll = fmaf(p.f0.t[j], xll[ix], r0ll);
+      }
+      // A = R1(hh) + R0(lh);  B = R1(hl) + R0(ll)   (absent inputs contribute exact zeros)
+      wA[S][e] = has_hi ? __fadd_rn(r1hh, r0lh) : 0.f;
+      wB[S][e] = has_hi ? (has_ll ? __fadd_rn(r1hl, r0ll) : r1hl) : r0ll;
+    }
+  }
+  if (emit) {
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr) {
+      float o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < L1; ++j) a = fmaf(p.f1.t[j], wA[(2 * U - 2 * C::MS + dr - C::M1 + j + 4 * WR) % WR][e], a);
+#pragma unroll
+        for (int j = 0; j < L0; ++j) b = fmaf(p.f0.t[j], wB[(2 * U - 2 * C::MS + dr - C::M0 + j + 4 * WR) % WR][e], b);
+        o[e] = has_hi ? __fadd_rn(a, b) : b;
+      }
+      if (colvalid) store2(y_ptr + dr * p.outpitch, o[0], o[1], 2, false);
+    }
+    y_ptr += 2 * p.outpitch;
+  }
+}
+
+template <int L0, int L1, int U>
+__device__ __forceinline__ void i1_dispatch(int uu, const DtParams& p, const float* band, const float* llrow,
+                                            bool has_hi, bool has_ll, float (&wA)[I1Cfg<L0, L1>::WR][2],
+                                            float (&wB)[I1Cfg<L0, L1>::WR][2], bool emit, float*& y_ptr,
+                                            bool colvalid) {
+  if constexpr (U < I1Cfg<L0, L1>::UNR) {
+    if (uu == U) i1_stage<L0, L1, U>(p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid);
+    else i1_dispatch<L0, L1, U + 1>(uu, p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid);
+  }
+}
+
+template <int L0, int L1>
+__global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+                                                    int CH /* complex rows per chunk */) {
+  using C = I1Cfg<L0, L1>;
+  extern __shared__ __align__(16) float smem[];
+  float* ring = smem;
+  float* bandbuf = smem + C::NS * C::STAGE;
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+  const int n = plane / p.C, ch = plane - n * p.C;
+
+  const int H = p.H, W = p.W, h2 = H >> 1;
+  const int c0 = strip * 64;                         // first output (= quad-domain) column of the strip
+  const int i0 = chunk * CH;
+  const int i1 = imin(i0 + CH, h2);
+  const int n_stage = (i1 - i0) + C::PRO;
+  const int ncols = imin(64, W - c0);
+  const int c_a = c0 - C::HLA;
+  const int need_cols = C::HLA + ncols + C::M;
+  const bool has_hi = (p.highs != nullptr), has_ll = (p.in != nullptr);
+  const int sym = has_hi ? p.sym : 1;                // low-pass-only path ignores `mode` (reference :159)
+  const int mode = sym ? B200W_MODE_SYMMETRIC : B200W_MODE_ZERO;
+
+  const float* hbase = has_hi ? p.highs + n * p.hs[0] + ch * p.hs[1] : nullptr;
+  const float* llp = has_ll ? p.in + (long long)plane * p.inps : nullptr;
+
+  // zero ring + band buffer once (absent inputs / never-copied columns must read as zeros)
+  for (int i = lane; i < C::NS * C::STAGE + C::BAND; i += 32) smem[i] = 0.f;
+  __syncwarp();
+
+  // static copy schedule: chunk -> (virtual row v, column chunk cc)
+  int c_soff[C::NCH], c_gcol[C::NCH], c_v[C::NCH];
+#pragma unroll
+  for (int k = 0; k < C::NCH; ++k) {
+    const int chn = lane + 32 * k;
+    const int v = chn / C::CPR;
+    const int cc = chn - v * C::CPR;
+    const int gc = c_a + 4 * cc;
+    const bool on = (chn < C::VR * C::CPR) && (4 * cc < need_cols) && (gc >= 0) && (gc + 3 < W) &&
+                    ((v < 6) ? has_hi : has_ll);
+    c_soff[k] = on ? v * C::SW + 4 * cc : -1;
+    c_gcol[k] = gc;
+    c_v[k] = v;
+  }
+  // border fix-ups in the real (quad) domain: 6 band rows (bandbuf) + 2 ll rows (ring rows 6,7)
+  const int nleft = imin(imax(0, -c_a), need_cols);
+  const int sr0 = imax(W - c_a, 0);
+  const int nright = imax(0, need_cols - sr0);
+  const int nb_row = nleft + nright;
+  int fix_dst[C::NFIX], fix_src[C::NFIX];
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < C::NFIX; ++q) {
+    fix_dst[q] = -1;
+    fix_src[q] = -1;
+    const int e = lane + 32 * q;
+    if (e < 8 * nb_row) {
+      const int v = e / (nb_row > 0 ? nb_row : 1);   // 0..5 band rows, 6..7 ll rows
+      const int idx = e - v * nb_row;
+      const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
+      const int g = sym_or_zero(c_a + sidx, W, sym);
+      fix_dst[q] = v * C::SW + sidx;
+      if (g >= 0) {
+        const int ss = g - c_a;
+        if (ss < 0 || ss >= need_cols) bad = true;
+        fix_src[q] = v * C::SW + ss;
+      }
+    }
+  }
+  // (a strip narrower than the filter halo would need sources outside the strip: such images go to the generic kernel)
+  const bool any_fix = (nb_row > 0) && !__any_sync(0xffffffffu, bad);
+
+  auto issue = [&](int t) {
+    if (t < n_stage) {
+      float* dst = ring + (t % C::NS) * C::STAGE;
+      const int ic = i0 - C::MS + t;                   // complex row of this stage (may be outside the image)
+      // quad rows 2ic, 2ic+1 under the extension: mirrored complex row with the row parity swapped
+      int ir = ic;
+      if (ic < 0) ir = -1 - ic; else if (ic >= h2) ir = 2 * h2 - 1 - ic;
+      const bool row_ok = (ic >= 0 && ic < h2) || (sym && ir >= 0 && ir < h2);
+      const int r0 = sym_or_zero(2 * ic, H, sym), r1 = sym_or_zero(2 * ic + 1, H, sym);
+#pragma unroll
+      for (int k = 0; k < C::NCH; ++k) {
+        if (c_soff[k] < 0) continue;
+        const int v = c_v[k];
+        float* d = dst + c_soff[k];
+        if (v < 6) {
+          if (row_ok) cp_async16(d, hbase + (long long)v * p.hs[2] + (long long)ir * p.hs[3] + c_gcol[k]);
+          else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const int rq = (v == 6) ? r0 : r1;
+          if (rq >= 0) cp_async16(d, llp + (long long)rq * p.inpitch + c_gcol[k]);
+          else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int t = 0; t < C::NS - 1; ++t) issue(t);
+
+  float wA[C::WR][2], wB[C::WR][2];
+#pragma unroll
+  for (int j = 0; j < C::WR; ++j) { wA[j][0] = wA[j][1] = wB[j][0] = wB[j][1] = 0.f; }
+
+  const bool colvalid = (c0 + 2 * lane) < W;
+  float* y_ptr = p.out + (long long)plane * p.outps + (long long)(2 * i0) * p.outpitch + c0 + 2 * lane;
+
+  int uu = 0;
+#pragma unroll 1
+  for (int t = 0; t < n_stage; ++t) {
+    cp_async_wait<C::NS - 2>();
+    __syncwarp();
+    float* stage = ring + (t % C::NS) * C::STAGE;
+    const int ic = i0 - C::MS + t;
+    const bool swap = (ic < 0 || ic >= h2);            // extended rows: row parity swapped
+    if (has_hi) {
+      // c2q: every lane converts its own complex column, lanes < 2*NHALO one halo column each
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        int qc;                                        // staged complex column index (float offset 2*qc)
+        if (part == 0) qc = C::NHALO + lane;
+        else if (lane < C::NHALO) qc = lane;
+        else if (lane < 2 * C::NHALO) qc = C::NHALO + 32 + (lane - C::NHALO);
+        else break;
+        const float* s = stage + 2 * qc;
+        const float2 w0 = *reinterpret_cast<const float2*>(s + 0 * C::SW);
+        const float2 w1 = *reinterpret_cast<const float2*>(s + 1 * C::SW);
+        const float2 w2 = *reinterpret_cast<const float2*>(s + 2 * C::SW);
+        const float2 w3 = *reinterpret_cast<const float2*>(s + 3 * C::SW);
+        const float2 w4 = *reinterpret_cast<const float2*>(s + 4 * C::SW);
+        const float2 w5 = *reinterpret_cast<const float2*>(s + 5 * C::SW);
+        // band <- (w1, w2) pairs: lh <- (o0, o5), hl <- (o2, o3), hh <- (o1, o4)   (transform_funcs.py:91-93)
+        const float2 p1[3] = {w0, w2, w1}, p2[3] = {w5, w3, w4};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const float a_ = __fmul_rn(__fadd_rn(p1[b].x, p2[b].x), kInvSqrt2);   // (row 0, col 0)
+          const float b_ = __fmul_rn(__fadd_rn(p1[b].y, p2[b].y), kInvSqrt2);   // (row 0, col 1)
+          const float c_ = __fmul_rn(__fsub_rn(p1[b].y, p2[b].y), kInvSqrt2);   // (row 1, col 0)
+          const float d_ = __fmul_rn(__fsub_rn(p2[b].x, p1[b].x), kInvSqrt2);   // (row 1, col 1)
+          float* o0 = bandbuf + (b * 2 + (swap ? 1 : 0)) * C::SW + 2 * qc;
+          float* o1 = bandbuf + (b * 2 + (swap ? 0 : 1)) * C::SW + 2 * qc;
+          *reinterpret_cast<float2*>(o0) = make_float2(a_, b_);
+          *reinterpret_cast<float2*>(o1) = make_float2(c_, d_);
+        }
+      }
+      __syncwarp();
+    }
+    if (any_fix) {
+#pragma unroll
+      for (int q = 0; q < C::NFIX; ++q) {
+        if (fix_dst[q] < 0) continue;
+        const bool is_ll = fix_dst[q] >= 6 * C::SW;
+        float* basep = is_ll ? stage : bandbuf;        // ll rows live in the ring at virtual rows 6,7
+        if (is_ll ? has_ll : has_hi) basep[fix_dst[q]] = (fix_src[q] >= 0) ? basep[fix_src[q]] : 0.f;
+      }
+      __syncwarp();
+    }
+    issue(t + C::NS - 1);
+    i1_dispatch<L0, L1, 0>(uu, p, bandbuf + 2 * lane, stage + 6 * C::SW + 2 * lane, has_hi, has_ll, wA, wB,
+                           t >= C::PRO, y_ptr, colvalid);
+    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+    __syncwarp();   // band buffer is rewritten by the next stage's c2q
+  }
+  cp_async_wait<0>();
+}
+
+template <int L0, int L1>
+inline int launch_i1_stream(const DtParams& p, cudaStream_t stream) {
+  using C = I1Cfg<L0, L1>;
+  if (p.highs) {
+    // band-pass rows must be plain complex rows: re/im adjacent, columns contiguous, 16-byte aligned
+    if (p.hs[5] != 1 || p.hs[4] != 2) return kNoFastPath;
+    if ((p.hs[0] | p.hs[1] | p.hs[2] | p.hs[3]) & 3) return kNoFastPath;
+    if (reinterpret_cast<uintptr_t>(p.highs) & 15) return kNoFastPath;
+  }
+  if (p.in && !aligned_plane(p.in, p.inps, p.inpitch)) return kNoFastPath;
+  if ((p.outpitch & 1) || (p.W & 3)) return kNoFastPath;
+  if (p.W < 2 * C::HLA) return kNoFastPath;
+  const int n_strips = (p.W + 63) / 64;
+  const long long planes = (long long)p.N * p.C;
+  int n_chunks, CH;
+  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  const long long blocks = planes * n_strips * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return kNoFastPath;
+  inv_j1_stream<L0, L1><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
+  return 0;
+}
+
+inline int try_launch_inv_j1(const DtParams& p, cudaStream_t stream) {
+  if (g_force_generic) return kNoFastPath;
+  if ((long long)p.N * p.C == 0) return 0;
+  if (p.L0 == 7 && p.L1 == 5) return launch_i1_stream<7, 5>(p, stream);   // near_sym_a synthesis
+  if (p.L0 == 5 && p.L1 == 7) return launch_i1_stream<5, 7>(p, stream);   // near_sym_a analysis (backward of fwd)
+  return kNoFastPath;
+}
