@@ -154,6 +154,8 @@ int b200w_dtcwt_inv_j2plus(const float* ll, long long ll_plane_stride, int ll_pi
   int rc = build_inv_j2plus(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W,
                             g0a, g1a, g0b, g1b, m);
   if (rc) return rc;
+  rc = fast::try_launch_inv_j2plus(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
   return launch_tile(k_inv_j2plus_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj2_smem_floats(m), stream);
 }
 

@@ -237,6 +237,9 @@ inline int try_launch_sfb(const SfbParams& p, cudaStream_t stream) {
 // Requires the default band-pass layout along the row (re/im adjacent, columns contiguous) and 16-byte
 // aligned rows; everything else takes the generic kernel.
 // ================================================================================================
+template <int HLA, int NS, int MS>
+struct QuadStager;
+
 template <int L0, int L1>
 struct I1Cfg {
   static constexpr int M0 = L0 / 2, M1 = L1 / 2, M = (M0 > M1) ? M0 : M1;
@@ -251,13 +254,7 @@ struct I1Cfg {
   static constexpr int UNR = WR / 2;                 // window period in stages
   static constexpr int PRO = 2 * MS;
   static constexpr int NS = 3;
-  static constexpr int VR = 8;                       // staged rows per stage: 6 orientations + 2 ll rows
-  static constexpr int STAGE = VR * SW;
-  static constexpr int BAND = 6 * SW;                // c2q'd band rows: (lh, hl, hh) x 2 quad rows
-  static constexpr int NCH = (VR * CPR + 31) / 32;
-  static constexpr int NHALO = HLA / 2;              // halo complex columns per side
-  static constexpr int NFIX = (8 * 2 * HLA + 31) / 32;  // border fix-ups: 8 real rows x 2 sides x HLA cols
-  static constexpr int SMEM_BYTES = (NS * STAGE + BAND) * 4;
+  static constexpr int SMEM_BYTES = QuadStager<HLA, NS, MS>::SMEM_FLOATS * 4;
 };
 
 template <int L0, int L1, int U>
@@ -331,143 +328,147 @@ __device__ __forceinline__ void i1_dispatch(int uu, const DtParams& p, const flo
   }
 }
 
-template <int L0, int L1>
-__global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
-                                                    int CH /* complex rows per chunk */) {
-  using C = I1Cfg<L0, L1>;
-  extern __shared__ __align__(16) float smem[];
-  float* ring = smem;
-  float* bandbuf = smem + C::NS * C::STAGE;
-  const int lane = threadIdx.x;
-  long long item = blockIdx.x;
-  const int strip = (int)(item % n_strips);
-  item /= n_strips;
-  const int chunk = (int)(item % n_chunks);
-  const int plane = (int)(item / n_chunks);
-  const int n = plane / p.C, ch = plane - n * p.C;
+// ------------------------------------------------------------------------------------------------
+// QuadStager: shared front end of the two DTCWT inverse kernels.  Per stage = one complex row ic:
+//   ring rows 0..5 = the six orientation rows (complex, as stored), rows 6,7 = ll rows 2ic, 2ic+1;
+//   after landing, c2q turns the complex rows into three real band rows x two quad rows in `bandbuf`
+//   (row index b*2 + rr, b: 0 lh, 1 hl, 2 hh), and the out-of-image columns of all eight real rows
+//   are patched from their mirror (or zero).  Out-of-image complex rows are the mirrored row with the
+//   row parity swapped.  Staged window: columns [c0 - HLA, c0 + 64 + HLA).
+// ------------------------------------------------------------------------------------------------
+template <int HLA, int NS, int MS>
+struct QuadStager {
+  static constexpr int SW = HLA + 64 + HLA;
+  static constexpr int CPR = SW / 4;
+  static constexpr int VR = 8;
+  static constexpr int STAGE = VR * SW;
+  static constexpr int BAND = 6 * SW;
+  static constexpr int NCH = (VR * CPR + 31) / 32;
+  static constexpr int NHALO = HLA / 2;
+  static constexpr int NFIX = (8 * 2 * HLA + 31) / 32;
+  static constexpr int SMEM_FLOATS = NS * STAGE + BAND;
 
-  const int H = p.H, W = p.W, h2 = H >> 1;
-  const int c0 = strip * 64;                         // first output (= quad-domain) column of the strip
-  const int i0 = chunk * CH;
-  const int i1 = imin(i0 + CH, h2);
-  const int n_stage = (i1 - i0) + C::PRO;
-  const int ncols = imin(64, W - c0);
-  const int c_a = c0 - C::HLA;
-  const int need_cols = C::HLA + ncols + C::M;
-  const bool has_hi = (p.highs != nullptr), has_ll = (p.in != nullptr);
-  const int sym = has_hi ? p.sym : 1;                // low-pass-only path ignores `mode` (reference :159)
-  const int mode = sym ? B200W_MODE_SYMMETRIC : B200W_MODE_ZERO;
+  float* ring;
+  float* bandbuf;
+  const float* hbase;
+  const float* llp;
+  long long hs2, hs3;
+  int inpitch, H, W, h2, sym, i0, n_stage, lane;
+  bool has_hi, has_ll, any_fix;
+  int c_soff[NCH], c_gcol[NCH];
+  int fix_dst[NFIX], fix_src[NFIX];
 
-  const float* hbase = has_hi ? p.highs + n * p.hs[0] + ch * p.hs[1] : nullptr;
-  const float* llp = has_ll ? p.in + (long long)plane * p.inps : nullptr;
-
-  // zero ring + band buffer once (absent inputs / never-copied columns must read as zeros)
-  for (int i = lane; i < C::NS * C::STAGE + C::BAND; i += 32) smem[i] = 0.f;
-  __syncwarp();
-
-  // static copy schedule: chunk -> (virtual row v, column chunk cc)
-  int c_soff[C::NCH], c_gcol[C::NCH], c_v[C::NCH];
+  __device__ __forceinline__ void init(float* smem, const DtParams& p, int plane, int c0, int need_cols, int i0_,
+                                       int n_stage_, int lane_) {
+    ring = smem;
+    bandbuf = smem + NS * STAGE;
+    lane = lane_;
+    i0 = i0_;
+    n_stage = n_stage_;
+    H = p.H; W = p.W; h2 = p.H >> 1;
+    has_hi = (p.highs != nullptr);
+    has_ll = (p.in != nullptr);
+    const int n = plane / p.C, ch = plane - n * p.C;
+    hbase = has_hi ? p.highs + n * p.hs[0] + ch * p.hs[1] : nullptr;
+    llp = has_ll ? p.in + (long long)plane * p.inps : nullptr;
+    hs2 = p.hs[2]; hs3 = p.hs[3];
+    inpitch = p.inpitch;
+    sym = has_hi ? p.sym : 1;   // low-pass-only path ignores `mode` (reference transform_funcs.py:159)
+    const int c_a = c0 - HLA;
+    // zero ring + band buffer once (absent inputs / never-copied columns must read as zeros)
+    for (int i = lane; i < SMEM_FLOATS; i += 32) smem[i] = 0.f;
+    __syncwarp();
 #pragma unroll
-  for (int k = 0; k < C::NCH; ++k) {
-    const int chn = lane + 32 * k;
-    const int v = chn / C::CPR;
-    const int cc = chn - v * C::CPR;
-    const int gc = c_a + 4 * cc;
-    const bool on = (chn < C::VR * C::CPR) && (4 * cc < need_cols) && (gc >= 0) && (gc + 3 < W) &&
-                    ((v < 6) ? has_hi : has_ll);
-    c_soff[k] = on ? v * C::SW + 4 * cc : -1;
-    c_gcol[k] = gc;
-    c_v[k] = v;
-  }
-  // border fix-ups in the real (quad) domain: 6 band rows (bandbuf) + 2 ll rows (ring rows 6,7)
-  const int nleft = imin(imax(0, -c_a), need_cols);
-  const int sr0 = imax(W - c_a, 0);
-  const int nright = imax(0, need_cols - sr0);
-  const int nb_row = nleft + nright;
-  int fix_dst[C::NFIX], fix_src[C::NFIX];
-  bool bad = false;
+    for (int k = 0; k < NCH; ++k) {
+      const int chn = lane + 32 * k;
+      const int v = chn / CPR;
+      const int cc = chn - v * CPR;
+      const int gc = c_a + 4 * cc;
+      const bool on = (chn < VR * CPR) && (4 * cc < need_cols) && (gc >= 0) && (gc + 3 < W) &&
+                      ((v < 6) ? has_hi : has_ll);
+      c_soff[k] = on ? v * SW + 4 * cc : -1;
+      c_gcol[k] = gc;
+    }
+    const int nleft = imin(imax(0, -c_a), need_cols);
+    const int sr0 = imax(W - c_a, 0);
+    const int nright = imax(0, need_cols - sr0);
+    const int nb_row = nleft + nright;
+    bool bad = false;
 #pragma unroll
-  for (int q = 0; q < C::NFIX; ++q) {
-    fix_dst[q] = -1;
-    fix_src[q] = -1;
-    const int e = lane + 32 * q;
-    if (e < 8 * nb_row) {
-      const int v = e / (nb_row > 0 ? nb_row : 1);   // 0..5 band rows, 6..7 ll rows
-      const int idx = e - v * nb_row;
-      const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
-      const int g = sym_or_zero(c_a + sidx, W, sym);
-      fix_dst[q] = v * C::SW + sidx;
-      if (g >= 0) {
-        const int ss = g - c_a;
-        if (ss < 0 || ss >= need_cols) bad = true;
-        fix_src[q] = v * C::SW + ss;
+    for (int q = 0; q < NFIX; ++q) {
+      fix_dst[q] = -1;
+      fix_src[q] = -1;
+      const int e = lane + 32 * q;
+      if (e < 8 * nb_row) {
+        const int v = e / (nb_row > 0 ? nb_row : 1);   // 0..5 band rows, 6..7 ll rows
+        const int idx = e - v * nb_row;
+        const int sidx = (idx < nleft) ? idx : sr0 + (idx - nleft);
+        const int g = sym_or_zero(c_a + sidx, W, sym);
+        fix_dst[q] = v * SW + sidx;
+        if (g >= 0) {
+          const int ss = g - c_a;
+          if (ss < 0 || ss >= need_cols) bad = true;
+          fix_src[q] = v * SW + ss;
+        }
       }
     }
+    any_fix = (nb_row > 0) && !__any_sync(0xffffffffu, bad);
   }
-  // (a strip narrower than the filter halo would need sources outside the strip: such images go to the generic kernel)
-  const bool any_fix = (nb_row > 0) && !__any_sync(0xffffffffu, bad);
 
-  auto issue = [&](int t) {
+  __device__ __forceinline__ void issue(int t) {
     if (t < n_stage) {
-      float* dst = ring + (t % C::NS) * C::STAGE;
-      const int ic = i0 - C::MS + t;                   // complex row of this stage (may be outside the image)
-      // quad rows 2ic, 2ic+1 under the extension: mirrored complex row with the row parity swapped
+      float* dst = ring + (t % NS) * STAGE;
+      const int ic = i0 - MS + t;                    // complex row of this stage (may be outside the image)
       int ir = ic;
       if (ic < 0) ir = -1 - ic; else if (ic >= h2) ir = 2 * h2 - 1 - ic;
       const bool row_ok = (ic >= 0 && ic < h2) || (sym && ir >= 0 && ir < h2);
       const int r0 = sym_or_zero(2 * ic, H, sym), r1 = sym_or_zero(2 * ic + 1, H, sym);
 #pragma unroll
-      for (int k = 0; k < C::NCH; ++k) {
+      for (int k = 0; k < NCH; ++k) {
         if (c_soff[k] < 0) continue;
-        const int v = c_v[k];
+        const int v = c_soff[k] / SW;
         float* d = dst + c_soff[k];
         if (v < 6) {
-          if (row_ok) cp_async16(d, hbase + (long long)v * p.hs[2] + (long long)ir * p.hs[3] + c_gcol[k]);
+          if (row_ok) cp_async16(d, hbase + (long long)v * hs2 + (long long)ir * hs3 + c_gcol[k]);
           else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
           const int rq = (v == 6) ? r0 : r1;
-          if (rq >= 0) cp_async16(d, llp + (long long)rq * p.inpitch + c_gcol[k]);
+          if (rq >= 0) cp_async16(d, llp + (long long)rq * inpitch + c_gcol[k]);
           else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
     cp_async_commit();
-  };
+  }
+
+  __device__ __forceinline__ void prologue() {
 #pragma unroll 1
-  for (int t = 0; t < C::NS - 1; ++t) issue(t);
+    for (int t = 0; t < NS - 1; ++t) issue(t);
+  }
 
-  float wA[C::WR][2], wB[C::WR][2];
-#pragma unroll
-  for (int j = 0; j < C::WR; ++j) { wA[j][0] = wA[j][1] = wB[j][0] = wB[j][1] = 0.f; }
-
-  const bool colvalid = (c0 + 2 * lane) < W;
-  float* y_ptr = p.out + (long long)plane * p.outps + (long long)(2 * i0) * p.outpitch + c0 + 2 * lane;
-
-  int uu = 0;
-#pragma unroll 1
-  for (int t = 0; t < n_stage; ++t) {
-    cp_async_wait<C::NS - 2>();
+  // wait for stage t, c2q it into bandbuf, patch borders; returns the ring stage (ll rows at rows 6,7)
+  __device__ __forceinline__ float* acquire(int t) {
+    cp_async_wait<NS - 2>();
     __syncwarp();
-    float* stage = ring + (t % C::NS) * C::STAGE;
-    const int ic = i0 - C::MS + t;
-    const bool swap = (ic < 0 || ic >= h2);            // extended rows: row parity swapped
+    float* stage = ring + (t % NS) * STAGE;
+    const int ic = i0 - MS + t;
+    const bool swap = (ic < 0 || ic >= h2);          // extended rows: row parity swapped
     if (has_hi) {
-      // c2q: every lane converts its own complex column, lanes < 2*NHALO one halo column each
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        int qc;                                        // staged complex column index (float offset 2*qc)
-        if (part == 0) qc = C::NHALO + lane;
-        else if (lane < C::NHALO) qc = lane;
-        else if (lane < 2 * C::NHALO) qc = C::NHALO + 32 + (lane - C::NHALO);
+        int qc;                                      // staged complex column (float offset 2*qc)
+        if (part == 0) qc = NHALO + lane;
+        else if (lane < NHALO) qc = lane;
+        else if (lane < 2 * NHALO) qc = NHALO + 32 + (lane - NHALO);
         else break;
-        const float* s = stage + 2 * qc;
-        const float2 w0 = *reinterpret_cast<const float2*>(s + 0 * C::SW);
-        const float2 w1 = *reinterpret_cast<const float2*>(s + 1 * C::SW);
-        const float2 w2 = *reinterpret_cast<const float2*>(s + 2 * C::SW);
-        const float2 w3 = *reinterpret_cast<const float2*>(s + 3 * C::SW);
-        const float2 w4 = *reinterpret_cast<const float2*>(s + 4 * C::SW);
-        const float2 w5 = *reinterpret_cast<const float2*>(s + 5 * C::SW);
-        // band <- (w1, w2) pairs: lh <- (o0, o5), hl <- (o2, o3), hh <- (o1, o4)   (transform_funcs.py:91-93)
+        const float* sp = stage + 2 * qc;
+        const float2 w0 = *reinterpret_cast<const float2*>(sp + 0 * SW);
+        const float2 w1 = *reinterpret_cast<const float2*>(sp + 1 * SW);
+        const float2 w2 = *reinterpret_cast<const float2*>(sp + 2 * SW);
+        const float2 w3 = *reinterpret_cast<const float2*>(sp + 3 * SW);
+        const float2 w4 = *reinterpret_cast<const float2*>(sp + 4 * SW);
+        const float2 w5 = *reinterpret_cast<const float2*>(sp + 5 * SW);
+        // band <- (w1, w2): lh <- (o0, o5), hl <- (o2, o3), hh <- (o1, o4)   (reference transform_funcs.py:91-93)
         const float2 p1[3] = {w0, w2, w1}, p2[3] = {w5, w3, w4};
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -475,8 +476,8 @@ __global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtPa
           const float b_ = __fmul_rn(__fadd_rn(p1[b].y, p2[b].y), kInvSqrt2);   // (row 0, col 1)
           const float c_ = __fmul_rn(__fsub_rn(p1[b].y, p2[b].y), kInvSqrt2);   // (row 1, col 0)
           const float d_ = __fmul_rn(__fsub_rn(p2[b].x, p1[b].x), kInvSqrt2);   // (row 1, col 1)
-          float* o0 = bandbuf + (b * 2 + (swap ? 1 : 0)) * C::SW + 2 * qc;
-          float* o1 = bandbuf + (b * 2 + (swap ? 0 : 1)) * C::SW + 2 * qc;
+          float* o0 = bandbuf + (b * 2 + (swap ? 1 : 0)) * SW + 2 * qc;
+          float* o1 = bandbuf + (b * 2 + (swap ? 0 : 1)) * SW + 2 * qc;
           *reinterpret_cast<float2*>(o0) = make_float2(a_, b_);
           *reinterpret_cast<float2*>(o1) = make_float2(c_, d_);
         }
@@ -485,16 +486,65 @@ __global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtPa
     }
     if (any_fix) {
 #pragma unroll
-      for (int q = 0; q < C::NFIX; ++q) {
+      for (int q = 0; q < NFIX; ++q) {
         if (fix_dst[q] < 0) continue;
-        const bool is_ll = fix_dst[q] >= 6 * C::SW;
-        float* basep = is_ll ? stage : bandbuf;        // ll rows live in the ring at virtual rows 6,7
+        const bool is_ll = fix_dst[q] >= 6 * SW;
+        float* basep = is_ll ? stage : bandbuf;      // ll rows live in the ring at virtual rows 6,7
         if (is_ll ? has_ll : has_hi) basep[fix_dst[q]] = (fix_src[q] >= 0) ? basep[fix_src[q]] : 0.f;
       }
       __syncwarp();
     }
-    issue(t + C::NS - 1);
-    i1_dispatch<L0, L1, 0>(uu, p, bandbuf + 2 * lane, stage + 6 * C::SW + 2 * lane, has_hi, has_ll, wA, wB,
+    return stage;
+  }
+};
+
+inline bool quad_inputs_ok(const DtParams& p) {
+  if (p.highs) {
+    // band-pass rows must be plain complex rows: re/im adjacent, columns contiguous, 16-byte aligned
+    if (p.hs[5] != 1 || p.hs[4] != 2) return false;
+    if ((p.hs[0] | p.hs[1] | p.hs[2] | p.hs[3]) & 3) return false;
+    if (reinterpret_cast<uintptr_t>(p.highs) & 15) return false;
+  }
+  if (p.in && !aligned_plane(p.in, p.inps, p.inpitch)) return false;
+  return (p.W & 3) == 0;
+}
+
+template <int L0, int L1>
+__global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+                                                    int CH /* complex rows per chunk */) {
+  using C = I1Cfg<L0, L1>;
+  using QS = QuadStager<C::HLA, C::NS, C::MS>;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+
+  const int c0 = strip * 64;                         // first output (= quad-domain) column of the strip
+  const int i0 = chunk * CH;
+  const int i1 = imin(i0 + CH, p.H >> 1);
+  const int n_stage = (i1 - i0) + C::PRO;
+  const int ncols = imin(64, p.W - c0);
+
+  QS qs;
+  qs.init(smem, p, plane, c0, C::HLA + ncols + C::M, i0, n_stage, lane);
+  qs.prologue();
+
+  float wA[C::WR][2], wB[C::WR][2];
+#pragma unroll
+  for (int j = 0; j < C::WR; ++j) { wA[j][0] = wA[j][1] = wB[j][0] = wB[j][1] = 0.f; }
+
+  const bool colvalid = (c0 + 2 * lane) < p.W;
+  float* y_ptr = p.out + (long long)plane * p.outps + (long long)(2 * i0) * p.outpitch + c0 + 2 * lane;
+
+  int uu = 0;
+#pragma unroll 1
+  for (int t = 0; t < n_stage; ++t) {
+    const float* stage = qs.acquire(t);
+    qs.issue(t + C::NS - 1);
+    i1_dispatch<L0, L1, 0>(uu, p, qs.bandbuf + 2 * lane, stage + 6 * C::SW + 2 * lane, qs.has_hi, qs.has_ll, wA, wB,
                            t >= C::PRO, y_ptr, colvalid);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
     __syncwarp();   // band buffer is rewritten by the next stage's c2q
@@ -505,15 +555,7 @@ __global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtPa
 template <int L0, int L1>
 inline int launch_i1_stream(const DtParams& p, cudaStream_t stream) {
   using C = I1Cfg<L0, L1>;
-  if (p.highs) {
-    // band-pass rows must be plain complex rows: re/im adjacent, columns contiguous, 16-byte aligned
-    if (p.hs[5] != 1 || p.hs[4] != 2) return kNoFastPath;
-    if ((p.hs[0] | p.hs[1] | p.hs[2] | p.hs[3]) & 3) return kNoFastPath;
-    if (reinterpret_cast<uintptr_t>(p.highs) & 15) return kNoFastPath;
-  }
-  if (p.in && !aligned_plane(p.in, p.inps, p.inpitch)) return kNoFastPath;
-  if ((p.outpitch & 1) || (p.W & 3)) return kNoFastPath;
-  if (p.W < 2 * C::HLA) return kNoFastPath;
+  if (!quad_inputs_ok(p) || (p.outpitch & 1) || p.W < 2 * C::HLA) return kNoFastPath;
   const int n_strips = (p.W + 63) / 64;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
@@ -530,5 +572,194 @@ inline int try_launch_inv_j1(const DtParams& p, cudaStream_t stream) {
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 7 && p.L1 == 5) return launch_i1_stream<7, 5>(p, stream);   // near_sym_a synthesis
   if (p.L0 == 5 && p.L1 == 7) return launch_i1_stream<5, 7>(p, stream);   // near_sym_a analysis (backward of fwd)
+  return kNoFastPath;
+}
+
+// ================================================================================================
+// K6 fast: DTCWT level >= 2 inverse (reference INV_J2PLUS.forward / inv_j2plus, transform_funcs.py:279-307).
+//   y = R_H(C_H(hh) + C_L(hl)) + R_L(C_H(lh) + C_L(ll)),  C/R = col/row interpolating q-shift filters
+//   (colifilt / rowifilt, dtcwt/lowlevel.py:154-239): out[4t+s] = sum_{j<m2} f_s[j] x[sym(2(t+j) + o_s - m2)],
+//   low call (ha,hb) = (g0b,g0a), high call (ha,hb) = (g1b,g1a) with the high-pass phase table.
+// W pass first on the staged rows (A = R_H(hh) + R_L(lh), B = R_H(hl) + R_L(ll), 4 output columns per lane),
+// H pass in the register window (y = C_H(A) + C_L(B), 4 output rows per stage).  Same front end as K5.
+//   taps: f0=g0a f1=g1a f2=g0b f3=g1b (stored).
+// ================================================================================================
+template <int M2, bool HP>
+struct IfPhase {  // dtcwt/lowlevel.py:169-186
+  static constexpr int par(int s) { return (M2 % 2 == 0) ? (s >= 2 ? 1 : 0) : (s < 2 ? 1 : 0); }
+  static constexpr int off(int s) {
+    return (M2 % 2 == 0) ? (HP ? (s ^ 1) : s) : (HP ? (2 - (s & 1)) : (1 + (s & 1)));
+  }
+  static constexpr int omin = (M2 % 2 == 0) ? 0 : 1;
+  static constexpr int omax = (M2 % 2 == 0) ? 3 : 2;
+};
+
+template <int MQ>
+struct I2Cfg {
+  static constexpr int M2 = MQ / 2;
+  static constexpr int OMIN = IfPhase<M2, false>::omin, OMAX = IfPhase<M2, false>::omax;
+  static constexpr int HL = M2 - OMIN;               // input columns needed left of 2u
+  static constexpr int HR = M2 + OMAX - 3;           // ... right of 2u+1
+  static constexpr int HMAX = (HL > HR) ? HL : HR;
+  static constexpr int HLA = (HMAX + 3) / 4 * 4;
+  static constexpr int SW = HLA + 64 + HLA;
+  static constexpr int OFFX = HLA - HL;
+  static constexpr int NX = OFFX + HL + 2 + HR;
+  static constexpr int NV2 = (NX + 1) / 2;
+  static constexpr int MS = (HMAX + 1) / 2;
+  static constexpr int WR = 4 * MS + 2;
+  static constexpr int UNR = WR / 2;
+  static constexpr int PRO = 2 * MS;
+  static constexpr int NS = 3;
+  static constexpr int SMEM_BYTES = QuadStager<HLA, NS, MS>::SMEM_FLOATS * 4;
+};
+
+template <int MQ, int U>
+__device__ __forceinline__ void i2_stage(const DtParams& p, const float* band, const float* llrow, bool has_hi,
+                                         bool has_ll, float (&wA)[I2Cfg<MQ>::WR][4], float (&wB)[I2Cfg<MQ>::WR][4],
+                                         bool emit, float*& y_ptr, bool colvalid, bool vec4) {
+  using C = I2Cfg<MQ>;
+  using PL = IfPhase<C::M2, false>;
+  using PH = IfPhase<C::M2, true>;
+  constexpr int WR = C::WR, M2 = C::M2;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    float xlh[2 * C::NV2], xhl[2 * C::NV2], xhh[2 * C::NV2], xll[2 * C::NV2];
+#pragma unroll
+    for (int q = 0; q < C::NV2; ++q) {
+      const float2 a = *reinterpret_cast<const float2*>(band + (0 * 2 + rr) * C::SW + 2 * q);
+      const float2 b = *reinterpret_cast<const float2*>(band + (1 * 2 + rr) * C::SW + 2 * q);
+      const float2 c = *reinterpret_cast<const float2*>(band + (2 * 2 + rr) * C::SW + 2 * q);
+      const float2 d = *reinterpret_cast<const float2*>(llrow + rr * C::SW + 2 * q);
+      xlh[2 * q] = a.x; xlh[2 * q + 1] = a.y;
+      xhl[2 * q] = b.x; xhl[2 * q + 1] = b.y;
+      xhh[2 * q] = c.x; xhh[2 * q + 1] = c.y;
+      xll[2 * q] = d.x; xll[2 * q + 1] = d.y;
+    }
+    const int S = (2 * U + rr) % WR;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      // s even -> ha, s odd -> hb;  low: ha=g0b(f2) hb=g0a(f0);  high: ha=g1b(f3) hb=g1a(f1)
+      const float* fl = (s & 1) ? p.f0.t : p.f2.t;
+      const float* fh = (s & 1) ? p.f1.t : p.f3.t;
+      float rh_hh = 0.f, rh_hl = 0.f, rl_lh = 0.f, rl_ll = 0.f;
+#pragma unroll
+      for (int j = 0; j < M2; ++j) {
+        const int ih = C::OFFX + 2 * j + (PH::off(s) - C::OMIN);
+        const int il = C::OFFX + 2 * j + (PL::off(s) - C::OMIN);
+        const float ch = fh[2 * j + PH::par(s)], cl = fl[2 * j + PL::par(s)];
+        rh_hh = fmaf(ch, xhh[ih], rh_hh);
+        rh_hl = fmaf(ch, xhl[ih], rh_hl);
+        rl_lh = fmaf(cl, xlh[il], rl_lh);
+        rl_ll = fmaf(cl, xll[il], rl_ll);
+      }
+      wA[S][s] = has_hi ? __fadd_rn(rh_hh, rl_lh) : 0.f;
+      wB[S][s] = has_hi ? (has_ll ? __fadd_rn(rh_hl, rl_ll) : rh_hl) : rl_ll;
+    }
+  }
+  if (emit) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {   // output row 4i + s
+      const float* fl = (s & 1) ? p.f0.t : p.f2.t;
+      const float* fh = (s & 1) ? p.f1.t : p.f3.t;
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < M2; ++j) {
+          const int sh = (2 * U - 2 * C::MS + 2 * j + PH::off(s) - M2 + 4 * WR) % WR;
+          const int sl = (2 * U - 2 * C::MS + 2 * j + PL::off(s) - M2 + 4 * WR) % WR;
+          a = fmaf(fh[2 * j + PH::par(s)], wA[sh][c], a);
+          b = fmaf(fl[2 * j + PL::par(s)], wB[sl][c], b);
+        }
+        o[c] = has_hi ? __fadd_rn(a, b) : b;
+      }
+      if (colvalid) {
+        float* q = y_ptr + s * p.outpitch;
+        if (vec4) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+        else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; q[3] = o[3]; }
+      }
+    }
+    y_ptr += 4 * p.outpitch;
+  }
+}
+
+template <int MQ, int U>
+__device__ __forceinline__ void i2_dispatch(int uu, const DtParams& p, const float* band, const float* llrow,
+                                            bool has_hi, bool has_ll, float (&wA)[I2Cfg<MQ>::WR][4],
+                                            float (&wB)[I2Cfg<MQ>::WR][4], bool emit, float*& y_ptr, bool colvalid,
+                                            bool vec4) {
+  if constexpr (U < I2Cfg<MQ>::UNR) {
+    if (uu == U) i2_stage<MQ, U>(p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid, vec4);
+    else i2_dispatch<MQ, U + 1>(uu, p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid, vec4);
+  }
+}
+
+template <int MQ>
+__global__ void __launch_bounds__(32) inv_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+                                                        int n_chunks, int CH /* complex rows per chunk */) {
+  using C = I2Cfg<MQ>;
+  using QS = QuadStager<C::HLA, C::NS, C::MS>;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x;
+  long long item = blockIdx.x;
+  const int strip = (int)(item % n_strips);
+  item /= n_strips;
+  const int chunk = (int)(item % n_chunks);
+  const int plane = (int)(item / n_chunks);
+
+  const int c0 = strip * 64;                         // first input (quad-domain) column of the strip
+  const int i0 = chunk * CH;
+  const int i1 = imin(i0 + CH, p.H >> 1);
+  const int n_stage = (i1 - i0) + C::PRO;
+  const int ncols = imin(64, p.W - c0);
+
+  QS qs;
+  qs.init(smem, p, plane, c0, C::HLA + ncols + C::HR, i0, n_stage, lane);
+  qs.prologue();
+
+  float wA[C::WR][4], wB[C::WR][4];
+#pragma unroll
+  for (int j = 0; j < C::WR; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { wA[j][c] = 0.f; wB[j][c] = 0.f; }
+
+  const bool colvalid = (c0 + 2 * lane) < p.W;
+  float* y_ptr = p.out + (long long)plane * p.outps + (long long)(4 * i0) * p.outpitch + 2 * c0 + 4 * lane;
+  const bool vec4 = ((p.outpitch & 3) == 0) && ((p.outps & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+
+  int uu = 0;
+#pragma unroll 1
+  for (int t = 0; t < n_stage; ++t) {
+    const float* stage = qs.acquire(t);
+    qs.issue(t + C::NS - 1);
+    i2_dispatch<MQ, 0>(uu, p, qs.bandbuf + 2 * lane, stage + 6 * C::SW + 2 * lane, qs.has_hi, qs.has_ll, wA, wB,
+                       t >= C::PRO, y_ptr, colvalid, vec4);
+    uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+}
+
+template <int MQ>
+inline int launch_i2_stream(const DtParams& p, cudaStream_t stream) {
+  using C = I2Cfg<MQ>;
+  if (!quad_inputs_ok(p) || p.W < 2 * C::HLA) return kNoFastPath;
+  const int n_strips = (p.W + 63) / 64;
+  const long long planes = (long long)p.N * p.C;
+  int n_chunks, CH;
+  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  const long long blocks = planes * n_strips * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) return kNoFastPath;
+  inv_j2plus_stream<MQ><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
+  return 0;
+}
+
+inline int try_launch_inv_j2plus(const DtParams& p, cudaStream_t stream) {
+  if (g_force_generic) return kNoFastPath;
+  if ((long long)p.N * p.C == 0) return 0;
+  if (p.L0 == 10) return launch_i2_stream<10>(p, stream);  // qshift_a, qshift_06
   return kNoFastPath;
 }
