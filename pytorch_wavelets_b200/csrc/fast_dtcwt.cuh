@@ -56,7 +56,7 @@ struct J1Cfg {
   static constexpr int PRO = M;
   static constexpr int NS = 4;
   static constexpr int NFIX = (2 * 2 * HLA + 31) / 32;
-  static constexpr int SMEM_BYTES = NS * 2 * SW * 4;
+  static constexpr int SMEM_BYTES = (NS * 2 * SW + 2 * NS) * 4;
   using Loader = StripLoader<2, SW, NS, NFIX>;
 };
 
@@ -253,7 +253,7 @@ struct J2Cfg {
   static constexpr int PRO = (MQ - 2) / 2;
   static constexpr int NS = 3;
   static constexpr int NFIX = (4 * 2 * HLA + 31) / 32;
-  static constexpr int SMEM_BYTES = NS * 4 * SW * 4;
+  static constexpr int SMEM_BYTES = (NS * 4 * SW + 2 * NS) * 4;
   using Loader = StripLoader<4, SW, NS, NFIX>;
 };
 

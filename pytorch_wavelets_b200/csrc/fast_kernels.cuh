@@ -40,6 +40,35 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- bulk async copies (the TMA engine's 1-D form, SASS UBLKCP) completing on an mbarrier ---------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(float* smem_dst, const float* gsrc, unsigned bytes, unsigned bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 // Boundary handling stays out of line: the hot loop must fit the instruction cache (an inlined
 // ext_index drags three integer modulo sequences per call into every unrolled stage).
 __device__ __noinline__ int ext_index_cold(int i, int N, int mode) { return ext_index(i, N, mode); }
@@ -92,7 +121,14 @@ struct StripLoader {
   static constexpr int CPR = SW / 4;
   static constexpr int NCH = (ROWS * CPR + 31) / 32;
   static constexpr int STAGE = ROWS * SW;  // floats per stage
+  // One plane per stage: each staged row is ONE bulk async copy (cp.async.bulk, the TMA engine) of its
+  // in-image part, completing on a per-stage mbarrier -- no per-lane address generation, no LDGSTS traffic.
+  static constexpr bool kBulk = (ROWS == RPP) && (ROWS <= 4);
+  static constexpr int SMEM_FLOATS = NS * STAGE + 2 * NS;  // ring + NS mbarriers (8 bytes each)
 
+  unsigned bar0;
+  int b_soff, b_goff, b_bytes;
+  bool bulk_on;
   float* ring;
   const float* plane;
   long long ps;
@@ -133,6 +169,23 @@ struct StripLoader {
     }
     use_cold = __any_sync(0xffffffffu, bad);
     any_fix = (nb_row > 0) && !use_cold;
+    {  // bulk path: the in-image part [cstart, cend) of every staged row, rounded to 16 bytes inside the pitch
+      const int cstart = imax(0, c_a);
+      const int cend = imin(c_a + (need_cols + 3) / 4 * 4, (W + 3) / 4 * 4);
+      b_soff = cstart - c_a;
+      b_goff = cstart;
+      b_bytes = (cend - cstart) * 4;
+      bulk_on = kBulk && !use_cold && (cend > cstart);
+      bar0 = (unsigned)__cvta_generic_to_shared(ring + NS * STAGE);
+      if (bulk_on) {
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) mbar_init(bar0 + 8 * i, 1);
+          mbar_fence_init();
+        }
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int ch = lane + 32 * k;
@@ -149,7 +202,29 @@ struct StripLoader {
     }
   }
 
+  __device__ __forceinline__ void issue_bulk(int t) {
+    if (t < n_stage) {
+      float* dst = ring + (t % NS) * STAGE;
+      const unsigned bar = bar0 + 8 * (t % NS);
+      const int r0 = r_begin + RPP * t;
+      int mine = -1, nvalid = 0;
+#pragma unroll
+      for (int v = 0; v < ROWS; ++v) {
+        const int r = r0 + v;
+        const int g = ((unsigned)r < (unsigned)H) ? r : ext_index_cold(r, H, mode);
+        if (g >= 0) ++nvalid;
+        else for (int i = lane; i < SW; i += 32) dst[v * SW + i] = 0.f;  // zero padding above / below the image
+        if (lane == v) mine = g;
+      }
+      fence_proxy_async();  // earlier generic-proxy writes to this slot (fix-ups, zero fill) before the async writes
+      if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)(nvalid * b_bytes));
+      if (lane < ROWS && mine >= 0)
+        bulk_copy_g2s(dst + lane * SW + b_soff, plane + (long long)mine * pitch + b_goff, (unsigned)b_bytes, bar);
+    }
+  }
+
   __device__ __forceinline__ void issue(int t) {
+    if (kBulk && bulk_on) { issue_bulk(t); return; }
     if (t < n_stage) {
       float* dst = ring + (t % NS) * STAGE;
       const int r0 = r_begin + RPP * t;
@@ -173,8 +248,13 @@ struct StripLoader {
 
   // wait for stage t, make it visible to the warp, patch the border columns; returns the stage base
   __device__ __forceinline__ float* acquire(int t) {
-    cp_async_wait<NS - 2>();
-    __syncwarp();
+    if (kBulk && bulk_on) {
+      __syncwarp();  // every lane is done with the slot the next issue() will overwrite
+      mbar_wait(bar0 + 8 * (t % NS), (unsigned)((t / NS) & 1));
+    } else {
+      cp_async_wait<NS - 2>();
+      __syncwarp();
+    }
     float* stage = ring + (t % NS) * STAGE;
     if (any_fix) {
 #pragma unroll
@@ -238,7 +318,7 @@ struct AfbCfg {
   static constexpr int RPS = 2 * HS;                 // image rows per stage
   static constexpr int NS = (HS == 4) ? 2 : ((HS == 2) ? 3 : 4);  // ring depth in stages
   static constexpr int NFIX = (PW == 32) ? (RPS * 2 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage
-  static constexpr int SMEM_BYTES = NS * RPS * G * SW * 4;
+  static constexpr int SMEM_BYTES = (NS * RPS * G * SW + 2 * NS) * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue half-stages before the first output row
   static constexpr int UNR = L / 2;                  // window period in half-stages
   static constexpr int UNS = UNR / HS;               // ... in stages: copies of the stage body
