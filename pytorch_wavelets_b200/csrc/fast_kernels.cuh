@@ -121,9 +121,15 @@ struct StripLoader {
   static constexpr int CPR = SW / 4;
   static constexpr int NCH = (ROWS * CPR + 31) / 32;
   static constexpr int STAGE = ROWS * SW;  // floats per stage
-  // One plane per stage: each staged row is ONE bulk async copy (cp.async.bulk, the TMA engine) of its
-  // in-image part, completing on a per-stage mbarrier -- no per-lane address generation, no LDGSTS traffic.
-  static constexpr bool kBulk = (ROWS == RPP) && (ROWS <= 4);
+  // Alternative staging (compile with -DB200W_BULK_STAGING=1): each staged row is ONE bulk async copy
+  // (cp.async.bulk, the TMA engine's 1-D form, SASS UBLKCP) of its in-image part, completing on a per-stage
+  // mbarrier -- no per-lane address generation, no LDGSTS traffic.  Measured on B200 it LOSES to the per-lane
+  // 16-byte cp.async schedule at this granularity (544-byte rows, 2 KB stages per warp): DWT level 1
+  // 2.31 vs 1.91 ms, level 2 0.81 vs 0.58 ms (profiles/r01_notes.md), so it is off by default.
+#ifndef B200W_BULK_STAGING
+#define B200W_BULK_STAGING 0
+#endif
+  static constexpr bool kBulk = (B200W_BULK_STAGING != 0) && (ROWS == RPP) && (ROWS <= 4);
   static constexpr int SMEM_FLOATS = NS * STAGE + 2 * NS;  // ring + NS mbarriers (8 bytes each)
 
   unsigned bar0;
