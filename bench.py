@@ -189,7 +189,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.005)
 
     def stop(self):
         self._halt.set()

@@ -9,11 +9,24 @@
 #include "launch_params.h"
 #include "fast_kernels.cuh"
 
+namespace b200w {
+constexpr int NT = 256;
+// ---- __global__ wrappers of the generic tile bodies ---------------------------------------------
+extern __shared__ __align__(16) float g_smem[];
+
+__global__ void __launch_bounds__(NT) k_afb2d_tile(const __grid_constant__ AfbParams p) { afb2d_tile<NT>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_sfb2d_tile(const __grid_constant__ SfbParams p) { sfb2d_tile<NT>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_fwd_j1_tile(const __grid_constant__ DtParams p) { fwd_j1_tile<NT, false>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_scat_j1_tile(const __grid_constant__ DtParams p) { fwd_j1_tile<NT, true>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_fwd_j2plus_tile(const __grid_constant__ DtParams p) { fwd_j2plus_tile<NT>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_inv_j1_tile(const __grid_constant__ DtParams p) { inv_j1_tile<NT>(p, blockIdx.x, g_smem); }
+__global__ void __launch_bounds__(NT) k_inv_j2plus_tile(const __grid_constant__ DtParams p) { inv_j2plus_tile<NT>(p, blockIdx.x, g_smem); }
+
+}  // namespace b200w
+
 using namespace b200w;
 
 namespace {
-
-constexpr int NT = 256;
 
 thread_local char g_last_cuda_error[256] = "";
 
@@ -38,17 +51,6 @@ int set_smem(K kernel, size_t bytes) {
   }
   return 0;
 }
-
-// ---- __global__ wrappers of the generic tile bodies ---------------------------------------------
-extern __shared__ __align__(16) float g_smem[];
-
-__global__ void __launch_bounds__(NT) k_afb2d_tile(const __grid_constant__ AfbParams p) { afb2d_tile<NT>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_sfb2d_tile(const __grid_constant__ SfbParams p) { sfb2d_tile<NT>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_fwd_j1_tile(const __grid_constant__ DtParams p) { fwd_j1_tile<NT, false>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_scat_j1_tile(const __grid_constant__ DtParams p) { fwd_j1_tile<NT, true>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_fwd_j2plus_tile(const __grid_constant__ DtParams p) { fwd_j2plus_tile<NT>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_inv_j1_tile(const __grid_constant__ DtParams p) { inv_j1_tile<NT>(p, blockIdx.x, g_smem); }
-__global__ void __launch_bounds__(NT) k_inv_j2plus_tile(const __grid_constant__ DtParams p) { inv_j2plus_tile<NT>(p, blockIdx.x, g_smem); }
 
 template <class K, class P>
 int launch_tile(K kernel, const P& p, long long blocks, int smem_floats, void* stream) {

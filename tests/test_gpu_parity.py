@@ -410,6 +410,38 @@ def test_dwt_linearity_and_pr_large():
     assert torch.equal(l3, ya[0]) and torch.equal(h1[0], ya[1][0]) and torch.equal(h3[0], ya[1][2])
 
 
+def test_config5_shape_db8_j4_zero():
+    """BASELINE.json configs[4] per-GPU shard shape (db8, J=4, mode zero, 2048x2048), reduced batch: bit-identity
+    with the oracle on one plane, pyramid shapes of SURVEY appendix A, perfect reconstruction."""
+    torch.manual_seed(15)
+    f = pw.DWTForward(J=4, wave='db8', mode='zero').to(DEV)
+    i = pw.DWTInverse(wave='db8', mode='zero').to(DEV)
+    x = torch.randn(2, 3, 2048, 2048, device=DEV)
+    yl, yh = f(x)
+    assert tuple(yl.shape) == (2, 3, 142, 142)
+    assert [tuple(h.shape[-2:]) for h in yh] == [(1031, 1031), (523, 523), (269, 269), (142, 142)]
+    hf = [_n(b) for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    oyl, oyh = orc.dwt_forward(_n(x[:1, :1]), hf, 4, 'zero')
+    assert np.array_equal(_n(yl[:1, :1]), oyl)
+    for a, b in zip(yh, oyh):
+        assert np.array_equal(_n(a[:1, :1]), b)
+    assert (i((yl, yh)) - x).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 2, 256, 256), (1, 3, 255, 130)])
+def test_periodization_roundtrip_and_oracle(shape):
+    torch.manual_seed(16)
+    x = torch.randn(*shape)
+    f = pw.DWTForward(J=3, wave='db4', mode='periodization')
+    hf = [b.numpy() for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    oyl, oyh = orc.dwt_forward(x.numpy(), hf, 3, 'periodization')
+    yl, yh = f.to(DEV)(x.to(DEV))
+    assert np.array_equal(_n(yl), oyl)
+    y = pw.DWTInverse(wave='db4', mode='periodization').to(DEV)((yl, yh))
+    H, W = shape[2:]
+    assert (y[:, :, :H, :W].cpu() - x).abs().max() < 2e-5
+
+
 def test_dtcwt_pr_and_energy_large():
     torch.manual_seed(12)
     f = pw.DTCWTForward(J=3).to(DEV)
