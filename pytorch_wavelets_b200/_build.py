@@ -37,11 +37,14 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """Compile the library.  ``out`` / ``extra_flags`` build an experimental variant next to the default one
+    (tools/variants.py); the package itself only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
+    target = out or SO
+    if out is None and not force and not needs_build():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-o', target] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc wants the system g++
     env.pop('CC', None)
@@ -51,7 +54,7 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed:\n' + r.stdout)
     if verbose:
         print(r.stdout)
-    return SO
+    return target
 
 
 if __name__ == '__main__':

@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, 'libb200wave.so')
+# B200W_LIB: load an experimental build of the same library instead (tools/variants.py); still CUDA-only.
+SO_PATH = os.environ.get('B200W_LIB') or os.path.join(_HERE, 'libb200wave.so')
 _lib = None
 
 c_ll = ctypes.c_longlong

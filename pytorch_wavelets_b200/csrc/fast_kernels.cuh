@@ -26,9 +26,22 @@ static int g_force_generic = 0;
 static int g_tune_minb = 0;
 static int g_tune_hs = 0;
 
+// experiment switches (see tools/variants.py): L2 prefetch qualifier of the staging copies, streaming stores
+#ifndef B200W_CPASYNC_L2
+#define B200W_CPASYNC_L2 0
+#endif
+#ifndef B200W_STREAM_STORES
+#define B200W_STREAM_STORES 1
+#endif
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if B200W_CPASYNC_L2 == 256
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#elif B200W_CPASYNC_L2 == 128
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -274,6 +287,7 @@ struct StripLoader {
 
 // store two adjacent outputs of one lane; nv = how many of them are inside the row (0..2)
 __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, bool stream) {
+  stream = stream && (B200W_STREAM_STORES != 0);
   if (nv == 2 && ((reinterpret_cast<uintptr_t>(ptr) & 7) == 0)) {
     if (stream) __stcs(reinterpret_cast<float2*>(ptr), make_float2(v0, v1));
     else *reinterpret_cast<float2*>(ptr) = make_float2(v0, v1);

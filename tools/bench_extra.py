@@ -33,4 +33,11 @@ with torch.no_grad():
     out['dwt_fwd_gpix_s'] = 128*32*512*512 / out['dwt_fwd_ms'] / 1e6; out['dwt_inv_gpix_s'] = 128*32*512*512 / out['dwt_inv_ms'] / 1e6
     out['dtcwt_fwd_gpix_s'] = 64*3*1024*1024 / out['dtcwt_fwd_ms'] / 1e6; out['dtcwt_inv_gpix_s'] = 64*3*1024*1024 / out['dtcwt_inv_ms'] / 1e6
     out['scat2_gpix_s'] = 256*3*256*256 / out['scat2_ms'] / 1e6
+    del x
+    # BASELINE configs[4] per-GPU shard shape (reduced batch): DWT J=4 db8 zero on 2048x2048
+    x = torch.randn(8, 16, 2048, 2048, device=dev)
+    f = pw.DWTForward(J=4, wave='db8', mode='zero').to(dev); g = pw.DWTInverse(wave='db8', mode='zero').to(dev)
+    c = f(x)
+    out['c5_dwt_fwd_ms'] = timeit(lambda: f(x)); out['c5_dwt_inv_ms'] = timeit(lambda: g(c))
+    out['c5_dwt_fwd_gpix_s'] = x.numel() / out['c5_dwt_fwd_ms'] / 1e6; out['c5_dwt_inv_gpix_s'] = x.numel() / out['c5_dwt_inv_ms'] / 1e6
 print(json.dumps({k: round(v, 4) for k, v in out.items()}))
