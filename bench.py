@@ -291,8 +291,16 @@ def run_ours(args):
     if calls:
         top = max(calls.values(), key=lambda c: c['total_ms'])
         ach = top['alg_bytes'] / (top['avg_ms'] / 1e3) / 1e9
+        # DRAM bytes of one launch of that kernel, from the committed ncu --set full capture (not measurable live)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            if top['tag'] in tj and args.dwt_batch == DWT_SHAPE[0]:
+                traffic = tj[top['tag']]['dram_bytes_per_launch']
+        except Exception:
+            pass
         roof = {'bound': 'hbm', 'kernel': top['tag'], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': ach / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'alg_bytes_per_launch': top['alg_bytes'], 'avg_launch_ms': top['avg_ms'],
                 'share_of_step': top['total_ms'] / (1e3 * (t_d + t_t)),
                 'whole_transform': {
