@@ -497,10 +497,12 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   if (blocks > 2147483647LL) return B200W_ESIZE;
   // tuning knobs (experiments): register cap MINB and rows per stage (HSM half-stages)
   if (g_tune_hs == 4) {
-    if (g_tune_minb == 24) launch_afb_kernel<L, PW, 24, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-    else launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   } else {
-    launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    // default: cap the allocation at 20 resident warps/SM for the short filters (94 registers, no spills, measured
+    // equal or better than the uncapped 118); long filters need their registers
+    if (g_tune_minb == 1 || L > 8) launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    else launch_afb_kernel<L, PW, 20, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   }
   return 0;
 }

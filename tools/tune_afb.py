@@ -8,7 +8,7 @@ L.b200w_debug_set_minb.argtypes = [ctypes.c_int]
 x = torch.randn(128, 32, 512, 512, device='cuda')
 f = pw.DWTForward(J=3, wave='db4', mode='symmetric').cuda()
 L.b200w_debug_set_hs.argtypes = [ctypes.c_int]
-for hs, minb in ((2, 0), (4, 0), (4, 24), (2, 0), (4, 0), (4, 24)):
+for hs, minb in ((2, 0), (2, 1), (4, 0), (2, 0), (2, 1), (4, 0)):
     L.b200w_debug_set_minb(minb); L.b200w_debug_set_hs(hs)
     with torch.no_grad():
         for _ in range(3): f(x)
