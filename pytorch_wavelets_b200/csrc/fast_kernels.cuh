@@ -127,8 +127,10 @@ __device__ __noinline__ void load_stage_general(float* dst, int rows, int rpp, i
 //   - rows outside the image / exotic modes go through load_stage_general (out of line).
 // The caller guarantees: plane base 16-byte aligned, pitch % 4 == 0, c_a % 4 == 0, SW % 4 == 0.
 // ================================================================================================
-template <int ROWS, int SW, int NS, int NFIX, int RPP = ROWS>
+template <int ROWS, int SW, int NS, int NFIX, int RPP = ROWS, bool GSRC = false>
 struct StripLoader {
+  // GSRC: border elements whose source column lies outside the staged strip (wrap-around modes) are fetched
+  // from global memory with the stage; without it such a strip falls back to the element-wise general loader.
   // ROWS "virtual" rows per stage = (ROWS / RPP) planes x RPP image rows: a warp working on a narrow
   // remainder strip stages the same rows of several planes at once (lanes are split between planes).
   static constexpr int CPR = SW / 4;
@@ -181,8 +183,12 @@ struct StripLoader {
         fix_dst[q] = v * SW + sidx;
         if (g >= 0) {
           const int ss = g - c_a;
-          if (ss < 0 || ss >= need_cols) bad = true;
-          fix_src[q] = v * SW + ss;
+          // the mirrored / wrapped source column is staged too: patch from shared memory after landing;
+          // otherwise ('periodic', 'periodization': it is at the other end of the row) fetch it from global
+          // memory together with the stage -- encoded as -(column) - 2
+          if (ss >= 0 && ss < need_cols && g < W) fix_src[q] = v * SW + ss;
+          else if (GSRC) fix_src[q] = -g - 2;
+          else bad = true;
         }
       }
     }
@@ -252,9 +258,29 @@ struct StripLoader {
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
           if (c_soff[k] >= 0) cp_async16(dst + c_soff[k], src + c_goff[k]);
+        if (GSRC && any_fix) {
+#pragma unroll
+          for (int q = 0; q < NFIX; ++q)
+            if (fix_dst[q] >= 0 && fix_src[q] <= -2) {
+              const int v = fix_dst[q] / SW;
+              const int g = v / RPP, rr = v - g * RPP;
+              cp_async4(dst + fix_dst[q], src + (long long)g * ps + (long long)rr * pitch + (-fix_src[q] - 2));
+            }
+        }
       } else {
         load_stage_general(dst, ROWS, RPP, SW, CPR, plane, ps, nplanes, r0, H, W, pitch, mode, c_a, need_cols,
                            use_cold ? 1 : 0, lane);
+        if (GSRC && any_fix) {  // border elements whose source is elsewhere in the (remapped) row
+#pragma unroll
+          for (int q = 0; q < NFIX; ++q)
+            if (fix_dst[q] >= 0 && fix_src[q] <= -2) {
+              const int v = fix_dst[q] / SW;
+              const int g = v / RPP, rr = v - g * RPP;
+              const int gr = ext_index_cold(r0 + rr, H, mode);
+              if (gr < 0) dst[fix_dst[q]] = 0.f;
+              else cp_async4(dst + fix_dst[q], plane + (long long)g * ps + (long long)gr * pitch + (-fix_src[q] - 2));
+            }
+        }
       }
     }
     cp_async_commit();
@@ -278,7 +304,7 @@ struct StripLoader {
     if (any_fix) {
 #pragma unroll
       for (int q = 0; q < NFIX; ++q)
-        if (fix_dst[q] >= 0) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
+        if (fix_dst[q] >= 0 && fix_src[q] >= -1) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
       __syncwarp();
     }
     return stage;
@@ -322,16 +348,19 @@ inline bool aligned_plane(const void* base, long long ps, int pitch) {
 //   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
 //   stage = 2 input rows = 1 output row.
 // ================================================================================================
-template <int L, int PW = 32, int HSM = 2>
+template <int L, int PW = 32, int HSM = 2, bool PER = false>
 struct AfbCfg {
   // PW = column pairs per plane handled by one warp: 32 -> the warp owns one 64-column strip of one plane;
   // PW < 32 -> a narrow remainder strip, the warp's lanes are split over G = 32/PW planes.
   static constexpr int G = 32 / PW;
-  static constexpr int HLA = ((L - 2) + 3) / 4 * 4;  // left halo rounded up to 16 bytes
-  static constexpr int SW = HLA + 4 * PW;            // staged floats per row (per plane)
-  static constexpr int OFF = HLA - (L - 2);          // lane window offset inside its aligned read
+  // out[k] = sum_j f[j] xe[2k + j - PL]: PL = L-2, or L/2-1 for periodization (reference afb1d :134-154)
+  static constexpr int PL = PER ? (L - 1 - L / 2) : (L - 2);
+  static constexpr int HLA = (PL + 3) / 4 * 4;       // left halo rounded up to 16 bytes
+  static constexpr int OFF = HLA - PL;               // lane window offset inside its aligned read
   static constexpr int NX = OFF + L + 2;             // floats a lane needs per row
   static constexpr int NV = (NX + 3) / 4;            // ... as 128-bit loads
+  static constexpr int SW = 4 * (PW - 1) + 4 * NV;   // staged floats per row (per plane)
+  static constexpr int RH = L - 2 - PL;              // columns needed right of the last output's 2k+1
   // half-stages (2 input rows = 1 output row) per stage: the largest of 4, 2, 1 dividing the window period
   static constexpr int HS0 = ((L / 2) % 4 == 0) ? 4 : (((L / 2) % 2 == 0) ? 2 : 1);
   static constexpr int HS = (HS0 < HSM) ? HS0 : HSM;
@@ -342,18 +371,17 @@ struct AfbCfg {
   static constexpr int PRO = (L - 2) / 2;            // prologue half-stages before the first output row
   static constexpr int UNR = L / 2;                  // window period in half-stages
   static constexpr int UNS = UNR / HS;               // ... in stages: copies of the stage body
-  using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS>;
-  static_assert(4 * NV - 4 <= HLA || PW == 32, "lane window must stay inside its plane's staged segment");
+  using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS, true>;
 };
 
 // one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
 // the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
 // window period, so every window index is a compile-time constant: the window never moves.
-template <int L, int PW, int HSM, int U>
+template <int L, int PW, int HSM, bool PER, int U>
 __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
                                           bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
                                           int Wo, int nv) {
-  using C = AfbCfg<L, PW, HSM>;
+  using C = AfbCfg<L, PW, HSM, PER>;
   float xa[4 * C::NV], xb[4 * C::NV];
 #pragma unroll
   for (int q = 0; q < C::NV; ++q) {
@@ -402,36 +430,36 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
   }
 }
 
-template <int L, int PW, int HSM, int V>
+template <int L, int PW, int HSM, bool PER, int V>
 __device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, const float* s0, float (&wl)[L][2],
                                                    float (&wh)[L][2], int h0, int h_emit_end, float*& ll_ptr,
                                                    float*& hi_ptr, long long band, int llpitch, int Wo, int nv) {
-  using C = AfbCfg<L, PW, HSM>;
+  using C = AfbCfg<L, PW, HSM, PER>;
   if constexpr (V < C::UNS) {
     if (vv == V) {
       // h0 = index of this stage's first half-stage; output rows are emitted for PRO <= h < h_emit_end
-      afb_stage<L, PW, HSM, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage<L, PW, HSM, PER, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       if constexpr (C::HS >= 2)
-        afb_stage<L, PW, HSM, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
+        afb_stage<L, PW, HSM, PER, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       if constexpr (C::HS == 4) {
-        afb_stage<L, PW, HSM, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
+        afb_stage<L, PW, HSM, PER, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-        afb_stage<L, PW, HSM, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
+        afb_stage<L, PW, HSM, PER, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       }
     } else {
-      afb_stage_dispatch<L, PW, HSM, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage_dispatch<L, PW, HSM, PER, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
     }
   }
 }
 
 // strip0 / n_strips: the 64-column strips this launch covers (PW == 32), or the single remainder strip
 // starting at output column k_rem (PW < 32, n_strips == 1).
-template <int L, int PW, int MINB, int HSM>
+template <int L, int PW, int MINB, int HSM, bool PER>
 __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
                                                    int CH, int k_rem) {
-  using C = AfbCfg<L, PW, HSM>;
+  using C = AfbCfg<L, PW, HSM, PER>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
   long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
@@ -453,7 +481,7 @@ __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__
 
   typename C::Loader ld;
   ld.init(ring, p.x + (long long)plane0 * p.xps, p.xps, nplanes, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA,
-          C::HLA + 2 * nvalid, 2 * ky0 - (L - 2), n_stage, lane);
+          C::HLA + 2 * nvalid + C::RH, 2 * ky0 - C::PL, n_stage, lane);
   ld.prologue();
 
   float wl[L][2], wh[L][2];
@@ -472,18 +500,18 @@ __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    afb_stage_dispatch<L, PW, HSM, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
+    afb_stage_dispatch<L, PW, HSM, PER, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
                                  nv);
     vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }
   cp_async_wait<0>();
 }
 
-template <int L, int PW, int MINB, int HSM>
+template <int L, int PW, int MINB, int HSM, bool PER = false>
 inline void launch_afb_kernel(const AfbParams& p, cudaStream_t stream, long long blocks, int n_strips, int n_chunks,
                               int CH, int k_rem) {
-  using C = AfbCfg<L, PW, HSM>;
-  afb2d_stream<L, PW, MINB, HSM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+  using C = AfbCfg<L, PW, HSM, PER>;
+  afb2d_stream<L, PW, MINB, HSM, PER><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
 }
 
 template <int L, int PW>
@@ -495,6 +523,11 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   const long long blocks = groups * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return B200W_ESIZE;
+  if (p.mode == B200W_MODE_PERIODIZATION) {
+    if (L > 8) launch_afb_kernel<L, PW, 1, 2, true>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    else launch_afb_kernel<L, PW, 20, 2, true>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    return 0;
+  }
   // tuning knobs (experiments): register cap MINB and rows per stage (HSM half-stages)
   if (g_tune_hs == 4) {
     launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
@@ -521,7 +554,7 @@ inline int launch_afb_stream(const AfbParams& p, cudaStream_t stream) {
 
 inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
   if (g_force_generic) return kNoFastPath;
-  if (p.Lw != p.Lh || p.mode == B200W_MODE_PERIODIZATION) return kNoFastPath;
+  if (p.Lw != p.Lh) return kNoFastPath;
   if (p.planes == 0) return 0;
   switch (p.Lw) {
     case 2: return launch_afb_stream<2>(p, stream);
