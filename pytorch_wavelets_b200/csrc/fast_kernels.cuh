@@ -348,8 +348,11 @@ inline bool aligned_plane(const void* base, long long ps, int pitch) {
 //   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
 //   stage = 2 input rows = 1 output row.
 // ================================================================================================
-template <int L, int PW = 32, int HSM = 2, bool PER = false>
+// XM: 0 = zero / symmetric / reflect (border sources inside the strip), 1 = periodic, 2 = periodization
+// (wrap-around modes: border columns come from the other end of the row, fetched with the stage)
+template <int L, int PW = 32, int HSM = 2, int XM = 0>
 struct AfbCfg {
+  static constexpr bool PER = (XM == 2);
   // PW = column pairs per plane handled by one warp: 32 -> the warp owns one 64-column strip of one plane;
   // PW < 32 -> a narrow remainder strip, the warp's lanes are split over G = 32/PW planes.
   static constexpr int G = 32 / PW;
@@ -371,17 +374,17 @@ struct AfbCfg {
   static constexpr int PRO = (L - 2) / 2;            // prologue half-stages before the first output row
   static constexpr int UNR = L / 2;                  // window period in half-stages
   static constexpr int UNS = UNR / HS;               // ... in stages: copies of the stage body
-  using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS, true>;
+  using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS, (XM != 0)>;
 };
 
 // one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
 // the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
 // window period, so every window index is a compile-time constant: the window never moves.
-template <int L, int PW, int HSM, bool PER, int U>
+template <int L, int PW, int HSM, int XM, int U>
 __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
                                           bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
                                           int Wo, int nv) {
-  using C = AfbCfg<L, PW, HSM, PER>;
+  using C = AfbCfg<L, PW, HSM, XM>;
   float xa[4 * C::NV], xb[4 * C::NV];
 #pragma unroll
   for (int q = 0; q < C::NV; ++q) {
@@ -430,36 +433,36 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
   }
 }
 
-template <int L, int PW, int HSM, bool PER, int V>
+template <int L, int PW, int HSM, int XM, int V>
 __device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, const float* s0, float (&wl)[L][2],
                                                    float (&wh)[L][2], int h0, int h_emit_end, float*& ll_ptr,
                                                    float*& hi_ptr, long long band, int llpitch, int Wo, int nv) {
-  using C = AfbCfg<L, PW, HSM, PER>;
+  using C = AfbCfg<L, PW, HSM, XM>;
   if constexpr (V < C::UNS) {
     if (vv == V) {
       // h0 = index of this stage's first half-stage; output rows are emitted for PRO <= h < h_emit_end
-      afb_stage<L, PW, HSM, PER, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage<L, PW, HSM, XM, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       if constexpr (C::HS >= 2)
-        afb_stage<L, PW, HSM, PER, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
+        afb_stage<L, PW, HSM, XM, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       if constexpr (C::HS == 4) {
-        afb_stage<L, PW, HSM, PER, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
+        afb_stage<L, PW, HSM, XM, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-        afb_stage<L, PW, HSM, PER, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
+        afb_stage<L, PW, HSM, XM, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
                                         ll_ptr, hi_ptr, band, llpitch, Wo, nv);
       }
     } else {
-      afb_stage_dispatch<L, PW, HSM, PER, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage_dispatch<L, PW, HSM, XM, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
     }
   }
 }
 
 // strip0 / n_strips: the 64-column strips this launch covers (PW == 32), or the single remainder strip
 // starting at output column k_rem (PW < 32, n_strips == 1).
-template <int L, int PW, int MINB, int HSM, bool PER>
+template <int L, int PW, int MINB, int HSM, int XM>
 __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
                                                    int CH, int k_rem) {
-  using C = AfbCfg<L, PW, HSM, PER>;
+  using C = AfbCfg<L, PW, HSM, XM>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
   long long item = blockIdx.x;                    // one warp per CTA: no intra-CTA load imbalance
@@ -500,18 +503,18 @@ __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    afb_stage_dispatch<L, PW, HSM, PER, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
+    afb_stage_dispatch<L, PW, HSM, XM, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
                                  nv);
     vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }
   cp_async_wait<0>();
 }
 
-template <int L, int PW, int MINB, int HSM, bool PER = false>
+template <int L, int PW, int MINB, int HSM, int XM = 0>
 inline void launch_afb_kernel(const AfbParams& p, cudaStream_t stream, long long blocks, int n_strips, int n_chunks,
                               int CH, int k_rem) {
-  using C = AfbCfg<L, PW, HSM, PER>;
-  afb2d_stream<L, PW, MINB, HSM, PER><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+  using C = AfbCfg<L, PW, HSM, XM>;
+  afb2d_stream<L, PW, MINB, HSM, XM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
 }
 
 template <int L, int PW>
@@ -524,18 +527,21 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return B200W_ESIZE;
   if (p.mode == B200W_MODE_PERIODIZATION) {
-    if (L > 8) launch_afb_kernel<L, PW, 1, 2, true>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-    else launch_afb_kernel<L, PW, 20, 2, true>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    launch_afb_kernel<L, PW, 1, 2, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    return 0;
+  }
+  if (p.mode == B200W_MODE_PERIODIC) {
+    launch_afb_kernel<L, PW, 1, 2, 1>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
     return 0;
   }
   // tuning knobs (experiments): register cap MINB and rows per stage (HSM half-stages)
   if (g_tune_hs == 4) {
     launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   } else {
-    // default: cap the allocation at 20 resident warps/SM for the short filters (94 registers, no spills, measured
-    // equal or better than the uncapped 118); long filters need their registers
-    if (g_tune_minb == 1 || L > 8) launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-    else launch_afb_kernel<L, PW, 20, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    // register caps (__launch_bounds__(32, 18..32)) were measured: they speed the small levels up a little but cost
+    // 15 % on the large one, so the default is the uncapped allocation
+    if (g_tune_minb == 20 && L <= 8) launch_afb_kernel<L, PW, 20, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+    else launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   }
   return 0;
 }
