@@ -178,5 +178,6 @@ void b200w_debug_force_generic(int on) { fast::g_force_generic = on; }
 /* tuning knob for experiments: register cap of the DWT streaming kernel (0 = compiler default, 24, 32) */
 void b200w_debug_set_minb(int v) { fast::g_tune_minb = v; }
 void b200w_debug_set_hs(int v) { fast::g_tune_hs = v; }
+void b200w_debug_set_want(int v) { fast::g_tune_want = v; }
 
 }  // extern "C"

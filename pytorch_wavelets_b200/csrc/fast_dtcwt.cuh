@@ -211,7 +211,8 @@ inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = (p.W + 63) / 64;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  static const int conc = resident_warps(fwd_j1_stream<L0, L1, SCAT>, C::SMEM_BYTES);
+  pick_chunks(planes * n_strips, p.H >> 1, 8, 8, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
@@ -389,7 +390,8 @@ inline int launch_j2_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = ((p.W >> 2) + 31) / 32;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  pick_chunks(planes * n_strips, p.H >> 2, 4, &n_chunks, &CH);
+  static const int conc = resident_warps(fwd_j2plus_stream<MQ>, C::SMEM_BYTES);
+  pick_chunks(planes * n_strips, p.H >> 2, 4, 7, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;

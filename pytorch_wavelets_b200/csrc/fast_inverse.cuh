@@ -200,7 +200,8 @@ inline int launch_sfb_stream(const SfbParams& p, cudaStream_t stream) {
   using C = SfbCfg<L>;
   const int n_strips = (((p.Wo + 1) >> 1) + 63) / 64;
   int n_chunks, CH;
-  pick_chunks((long long)p.planes * n_strips, (p.Ho + 1) >> 1, 16, &n_chunks, &CH);
+  static const int conc = resident_warps(sfb2d_stream<L>, C::SMEM_BYTES);
+  pick_chunks((long long)p.planes * n_strips, (p.Ho + 1) >> 1, 16, L / 2 + 8, conc, &n_chunks, &CH);
   const long long blocks = (long long)p.planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
@@ -559,7 +560,8 @@ inline int launch_i1_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = (p.W + 63) / 64;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  static const int conc = resident_warps(inv_j1_stream<L0, L1>, C::SMEM_BYTES);
+  pick_chunks(planes * n_strips, p.H >> 1, 8, 8, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
@@ -749,7 +751,8 @@ inline int launch_i2_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = (p.W + 63) / 64;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  pick_chunks(planes * n_strips, p.H >> 1, 8, &n_chunks, &CH);
+  static const int conc = resident_warps(inv_j2plus_stream<MQ>, C::SMEM_BYTES);
+  pick_chunks(planes * n_strips, p.H >> 1, 8, 8, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;

@@ -25,6 +25,7 @@ constexpr int kNoFastPath = 1;
 static int g_force_generic = 0;
 static int g_tune_minb = 0;
 static int g_tune_hs = 0;
+static long long g_tune_want = 0;
 
 // experiment switches (see tools/variants.py): L2 prefetch qualifier of the staging copies, streaming stores
 #ifndef B200W_CPASYNC_L2
@@ -323,20 +324,49 @@ __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, b
   }
 }
 
-// how many row-chunks to split a plane into so that the grid fills the machine a few times over
-inline void pick_chunks(long long base_items, int rows_out, int min_rows, int* n_chunks, int* CH) {
-  const long long want = 148LL * 32 * 3;
-  int nc = 1;
-  if (base_items < want) {
-    nc = (int)((want + base_items - 1) / (base_items > 0 ? base_items : 1));
-    const int max_chunks = (rows_out + min_rows - 1) / min_rows;
-    if (nc > max_chunks) nc = max_chunks;
-    if (nc < 1) nc = 1;
+// Resident warps of a one-warp-per-CTA kernel on the whole GPU (cached per kernel by the caller).
+template <class K>
+inline int resident_warps(K kernel, int smem_bytes) {
+  int per_sm = 0, dev = 0, sms = 148;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem_bytes) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 16;
   }
-  int ch = (rows_out + nc - 1) / nc;
-  ch = (ch + min_rows - 1) / min_rows * min_rows;
-  *CH = ch;
-  *n_chunks = (rows_out + ch - 1) / ch;
+  if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+// How many row-chunks to split each (plane, strip) march into.  Cost model, in units of one output row of one
+// warp: every chunk pays `pro` extra rows (halo + pipeline fill + schedule set-up); the grid drains through `conc`
+// resident warps; the last wave leaves the machine partly idle for about half a chunk.  Calibrated on B200
+// against K1/K3/K4 timings at 1..10 chunks (profiles/r01_notes.md).
+inline void pick_chunks(long long base_items, int rows_out, int min_rows, int pro, int conc, int* n_chunks, int* CH) {
+  if (g_tune_want > 0) {  // experiments: the old fixed-target rule
+    int nc = 1;
+    if (base_items < g_tune_want) nc = (int)((g_tune_want + base_items - 1) / (base_items > 0 ? base_items : 1));
+    int ch = (rows_out + nc - 1) / (nc > 0 ? nc : 1);
+    ch = (ch + min_rows - 1) / min_rows * min_rows;
+    if (ch < min_rows) ch = min_rows;
+    *CH = ch;
+    *n_chunks = (rows_out + ch - 1) / ch;
+    return;
+  }
+  const int max_chunks = (rows_out + min_rows - 1) / min_rows;
+  double best = 0.0;
+  int best_ch = (rows_out + min_rows - 1) / min_rows * min_rows, best_nc = 1, last_ch = -1;
+  if (best_ch < min_rows) best_ch = min_rows;
+  for (int nc = 1; nc <= max_chunks && nc <= 64; ++nc) {
+    int ch = (rows_out + nc - 1) / nc;
+    ch = (ch + min_rows - 1) / min_rows * min_rows;
+    if (ch == last_ch) continue;
+    last_ch = ch;
+    const int n = (rows_out + ch - 1) / ch;
+    const double work = (double)base_items * (rows_out + (double)n * pro) / (conc > 0 ? conc : 1);
+    const double cost = work + 0.5 * (ch + pro);
+    if (nc == 1 || cost < best) { best = cost; best_ch = ch; best_nc = n; }
+  }
+  *CH = best_ch;
+  *n_chunks = best_nc;
 }
 
 inline bool aligned_plane(const void* base, long long ps, int pitch) {
@@ -522,7 +552,8 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   constexpr int G = 32 / PW;
   const long long groups = ((long long)p.planes + G - 1) / G;
   int n_chunks, CH;
-  pick_chunks(groups * n_strips, p.Ho, 16, &n_chunks, &CH);
+  static const int conc = resident_warps(afb2d_stream<L, PW, 1, 2, 0>, AfbCfg<L, PW, 2, 0>::SMEM_BYTES);
+  pick_chunks(groups * n_strips, p.Ho, 16, (L - 2) / 2 + 8, conc, &n_chunks, &CH);
   const long long blocks = groups * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return B200W_ESIZE;

@@ -40,4 +40,4 @@ with torch.no_grad():
     c = f(x)
     out['c5_dwt_fwd_ms'] = timeit(lambda: f(x)); out['c5_dwt_inv_ms'] = timeit(lambda: g(c))
     out['c5_dwt_fwd_gpix_s'] = x.numel() / out['c5_dwt_fwd_ms'] / 1e6; out['c5_dwt_inv_gpix_s'] = x.numel() / out['c5_dwt_inv_ms'] / 1e6
-print(json.dumps({k: round(v, 4) for k, v in out.items()}))
+print(json.dumps({k: (v if k.endswith('_err') else round(v, 4)) for k, v in out.items()}))
