@@ -93,6 +93,7 @@ int b200w_dwt_afb2d(const float* x, long long x_plane_stride, int x_pitch, float
   int rc = build_afb(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, planes, H, W, fw_lo,
                      fw_hi, Lw, fh_lo, fh_hi, Lh, mode);
   if (rc) return rc;
+  p.hipitch = fast::g_tune_hipitch;
   rc = fast::try_launch_afb(p, (cudaStream_t)stream);
   if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
   return launch_tile(k_afb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, afb_smem_floats(Lw, Lh), stream);
@@ -179,5 +180,7 @@ void b200w_debug_force_generic(int on) { fast::g_force_generic = on; }
 void b200w_debug_set_minb(int v) { fast::g_tune_minb = v; }
 void b200w_debug_set_hs(int v) { fast::g_tune_hs = v; }
 void b200w_debug_set_want(int v) { fast::g_tune_want = v; }
+void b200w_debug_set_hipitch(int v) { fast::g_tune_hipitch = v; }
+void b200w_debug_set_balanced(int v) { fast::g_tune_balanced = v; }
 
 }  // extern "C"

@@ -94,6 +94,7 @@ struct AfbParams {  // K1
   int planes, H, W, Ho, Wo, Lw, Lh, mode;
   int tiles_x, tiles_y;
   Taps fw_lo, fw_hi, fh_lo, fh_hi;
+  int hipitch;        // experiments only (streaming kernel): row pitch of the band-pass planes, 0 = Wo
 };
 
 struct SfbParams {  // K2

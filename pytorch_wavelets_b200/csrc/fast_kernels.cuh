@@ -18,6 +18,10 @@
 
 #include "common.h"
 
+#ifndef B200W_EXP
+#define B200W_EXP 0
+#endif
+
 namespace b200w {
 namespace fast {
 
@@ -26,6 +30,8 @@ static int g_force_generic = 0;
 static int g_tune_minb = 0;
 static int g_tune_hs = 0;
 static long long g_tune_want = 0;
+static int g_tune_hipitch = 0;
+static int g_tune_balanced = 0;
 
 // experiment switches (see tools/variants.py): L2 prefetch qualifier of the staging copies, streaming stores
 #ifndef B200W_CPASYNC_L2
@@ -43,6 +49,25 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 #else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
 #endif
+}
+// the same with the destination already a 32-bit shared-window address (the hot path keeps those in registers:
+// converting a generic pointer costs three instructions on sm_100 every time)
+__device__ __forceinline__ void cp_async16_s(unsigned s, const float* gsrc) {
+#if B200W_CPASYNC_L2 == 256
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#elif B200W_CPASYNC_L2 == 128
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ float lds_s(unsigned s) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(s) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_s(unsigned s, float v) {
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(s), "f"(v) : "memory");
 }
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -152,6 +177,8 @@ struct StripLoader {
   int b_soff, b_goff, b_bytes;
   bool bulk_on;
   float* ring;
+  unsigned ring_s;       // the ring's shared-window address
+  int slot_i, slot_a;    // ring slot of the next issue() / acquire() (stage t lives in slot t % NS)
   const float* plane;
   long long ps;
   int nplanes, H, W, pitch, mode, c_a, need_cols, r_begin, n_stage, lane;
@@ -164,6 +191,8 @@ struct StripLoader {
                                        int pitch_, int mode_, int c_a_, int need_cols_, int r_begin_, int n_stage_,
                                        int lane_) {
     ring = ring_; plane = plane_; ps = ps_; nplanes = nplanes_; H = H_; W = W_; pitch = pitch_; mode = mode_;
+    ring_s = (unsigned)__cvta_generic_to_shared(ring_);
+    slot_i = slot_a = 0;
     c_a = c_a_; need_cols = need_cols_; r_begin = r_begin_; n_stage = n_stage_; lane = lane_;
     const int nleft = imin(imax(0, -c_a), need_cols);
     const int sr0 = imax(W - c_a, 0);  // first staged column right of the image
@@ -251,15 +280,18 @@ struct StripLoader {
 
   __device__ __forceinline__ void issue(int t) {
     if (kBulk && bulk_on) { issue_bulk(t); return; }
+    const int slot = slot_i;
+    slot_i = (slot_i + 1 == NS) ? 0 : slot_i + 1;
     if (t < n_stage) {
-      float* dst = ring + (t % NS) * STAGE;
       const int r0 = r_begin + RPP * t;
       if (!use_cold && r0 >= 0 && r0 + RPP <= H) {
+        const unsigned dst_s = ring_s + slot * (STAGE * 4);
         const float* src = plane + (long long)r0 * pitch;
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
-          if (c_soff[k] >= 0) cp_async16(dst + c_soff[k], src + c_goff[k]);
+          if (c_soff[k] >= 0) cp_async16_s(dst_s + 4 * c_soff[k], src + c_goff[k]);
         if (GSRC && any_fix) {
+          float* dst = ring + slot * STAGE;
 #pragma unroll
           for (int q = 0; q < NFIX; ++q)
             if (fix_dst[q] >= 0 && fix_src[q] <= -2) {
@@ -269,6 +301,7 @@ struct StripLoader {
             }
         }
       } else {
+        float* dst = ring + slot * STAGE;
         load_stage_general(dst, ROWS, RPP, SW, CPR, plane, ps, nplanes, r0, H, W, pitch, mode, c_a, need_cols,
                            use_cold ? 1 : 0, lane);
         if (GSRC && any_fix) {  // border elements whose source is elsewhere in the (remapped) row
@@ -297,18 +330,28 @@ struct StripLoader {
     if (kBulk && bulk_on) {
       __syncwarp();  // every lane is done with the slot the next issue() will overwrite
       mbar_wait(bar0 + 8 * (t % NS), (unsigned)((t / NS) & 1));
-    } else {
-      cp_async_wait<NS - 2>();
-      __syncwarp();
+      float* stage = ring + (t % NS) * STAGE;
+      if (any_fix) {
+#pragma unroll
+        for (int q = 0; q < NFIX; ++q)
+          if (fix_dst[q] >= 0 && fix_src[q] >= -1) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
+        __syncwarp();
+      }
+      return stage;
     }
-    float* stage = ring + (t % NS) * STAGE;
+    cp_async_wait<NS - 2>();
+    __syncwarp();
+    const int slot = slot_a;
+    slot_a = (slot_a + 1 == NS) ? 0 : slot_a + 1;
     if (any_fix) {
+      const unsigned st_s = ring_s + slot * (STAGE * 4);
 #pragma unroll
       for (int q = 0; q < NFIX; ++q)
-        if (fix_dst[q] >= 0 && fix_src[q] >= -1) stage[fix_dst[q]] = (fix_src[q] >= 0) ? stage[fix_src[q]] : 0.f;
+        if (fix_dst[q] >= 0 && fix_src[q] >= -1)
+          sts_s(st_s + 4 * fix_dst[q], (fix_src[q] >= 0) ? lds_s(st_s + 4 * fix_src[q]) : 0.f);
       __syncwarp();
     }
-    return stage;
+    return ring + slot * STAGE;
   }
 };
 
@@ -324,16 +367,30 @@ __device__ __forceinline__ void store2(float* ptr, float v0, float v1, int nv, b
   }
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves, each an IEEE fma -- the same roundings as two
+// scalar fmaf, in one issue slot.  ptxas folds a duplicated scalar ({x, x}) into the broadcast operand form and
+// takes tap pairs / scalars straight from uniform registers, so the pairs cost no extra moves.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2_s(float x, float2 b, float2 c) { return ffma2(make_float2(x, x), b, c); }
+
 // Resident warps of a one-warp-per-CTA kernel on the whole GPU (cached per kernel by the caller).
 template <class K>
-inline int resident_warps(K kernel, int smem_bytes) {
+inline int resident_warps(K kernel, int smem_bytes, int threads = 32) {
   int per_sm = 0, dev = 0, sms = 148;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem_bytes) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes) != cudaSuccess || per_sm < 1) {
     (void)cudaGetLastError();
-    per_sm = 16;
+    per_sm = imax(1, 16 / (threads / 32));
   }
   if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return per_sm * sms;
+  return per_sm * (threads / 32) * sms;
 }
 
 // How many row-chunks to split each (plane, strip) march into.  Cost model, in units of one output row of one
@@ -373,6 +430,17 @@ inline bool aligned_plane(const void* base, long long ps, int pitch) {
   return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (pitch % 4 == 0) && (ps % 4 == 0);
 }
 
+// A narrow last strip can have mirrored border columns whose source lies LEFT of its staged window (Wo = 257: the
+// strip holds one output column, the mirror needs columns up to 6 to its left).  Instead of dropping to the
+// element-wise loader, stage `sh` more columns on the left (a multiple of 4, as far as the row stride allows).
+__device__ __noinline__ int widen_left(int c_a, int need, int W, int mode, int room) {
+  if (c_a + need <= W || c_a <= 0) return 0;
+  const int g = ext_index(c_a + need - 1, W, mode);  // source of the farthest border column (mirror modes)
+  if (g < 0 || g >= c_a) return 0;
+  const int sh = (c_a - g + 3) & ~3;
+  return (sh <= c_a && sh <= room) ? sh : 0;  // room: what the widest reading lane leaves of the row stride
+}
+
 // ================================================================================================
 // K1 fast: DWT analysis level, Lw == Lh == L (even), modes zero / symmetric / reflect / periodic.
 //   strip = 64 output columns per warp (2 per lane) = 128 input columns + (L-2) halo;
@@ -407,13 +475,26 @@ struct AfbCfg {
   using Loader = StripLoader<RPS * G, SW, NS, NFIX, RPS, (XM != 0)>;
 };
 
-// one stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
-// the column pass reading tap j from slot (2U+2+j) mod L, and the stores.  U is the position inside the
+// ---- where a finished output row goes -------------------------------------------------------------------------
+// DirectOut: straight from registers to global memory (each lane stores its two adjacent columns of each band).
+struct DirectOut {
+  float* ll_ptr; float* hi_ptr; long long band; int llpitch, Wo, nv;
+  __device__ __forceinline__ void row(float2 lo0, float2 lo1, float2 hi0, float2 hi1) {
+    // {column low-pass of (l, h)} = {ll, band 1}; {column high-pass} = {band 0, band 2}   (reference order lh, hl, hh)
+    store2(ll_ptr, lo0.x, lo1.x, nv, false);
+    store2(hi_ptr, hi0.x, hi1.x, nv, true);
+    store2(hi_ptr + band, lo0.y, lo1.y, nv, true);
+    store2(hi_ptr + 2 * band, hi0.y, hi1.y, nv, true);
+    ll_ptr += llpitch;
+    hi_ptr += Wo;
+  }
+};
+
+// one half-stage of compute: row pass on the two staged rows into window slots (2U, 2U+1) mod L, then (if emit)
+// the column pass reading tap j from slot (2U+2+j) mod L, and the output row.  U is the position inside the
 // window period, so every window index is a compile-time constant: the window never moves.
-template <int L, int PW, int HSM, int XM, int U>
-__device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float (&wl)[L][2], float (&wh)[L][2],
-                                          bool emit, float*& ll_ptr, float*& hi_ptr, long long band, int llpitch,
-                                          int Wo, int nv) {
+template <int L, int PW, int HSM, int XM, int U, class Out>
+__device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, float2 (&w)[L][2], bool emit, Out& out) {
   using C = AfbCfg<L, PW, HSM, XM>;
   float xa[4 * C::NV], xb[4 * C::NV];
 #pragma unroll
@@ -423,66 +504,53 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
     xa[4 * q] = a.x; xa[4 * q + 1] = a.y; xa[4 * q + 2] = a.z; xa[4 * q + 3] = a.w;
     xb[4 * q] = b.x; xb[4 * q + 1] = b.y; xb[4 * q + 2] = b.z; xb[4 * q + 3] = b.w;
   }
+  // window entries are {row-lowpass, row-highpass} pairs: one packed FMA per tap feeds both
   constexpr int SA = (2 * U) % L, SB = (2 * U + 1) % L;
 #pragma unroll
   for (int o = 0; o < 2; ++o) {
-    float la = 0.f, ha = 0.f, lb = 0.f, hb = 0.f;
+    float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      const float f0 = p.fw_lo.t[j], f1 = p.fw_hi.t[j];
-      la = fmaf(f0, xa[C::OFF + 2 * o + j], la);
-      ha = fmaf(f1, xa[C::OFF + 2 * o + j], ha);
-      lb = fmaf(f0, xb[C::OFF + 2 * o + j], lb);
-      hb = fmaf(f1, xb[C::OFF + 2 * o + j], hb);
+      const float2 f = make_float2(p.fw_lo.t[j], p.fw_hi.t[j]);
+      ra = ffma2_s(xa[C::OFF + 2 * o + j], f, ra);
+      rb = ffma2_s(xb[C::OFF + 2 * o + j], f, rb);
     }
-    wl[SA][o] = la; wh[SA][o] = ha;
-    wl[SB][o] = lb; wh[SB][o] = hb;
+    w[SA][o] = ra;
+    w[SB][o] = rb;
   }
   if (emit) {
-    float all[2], alh[2], ahl[2], ahh[2];
+    float2 lo[2], hi[2];  // column low-pass of {l, h} -> {ll, hl}; column high-pass -> {lh, hh}
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < L; ++j) {
-        const float f0 = p.fh_lo.t[j], f1 = p.fh_hi.t[j];
         constexpr int base = 2 * U + 2;
-        a0 = fmaf(f0, wl[(base + j) % L][o], a0);
-        a1 = fmaf(f1, wl[(base + j) % L][o], a1);
-        a2 = fmaf(f0, wh[(base + j) % L][o], a2);
-        a3 = fmaf(f1, wh[(base + j) % L][o], a3);
+        a0 = ffma2_s(p.fh_lo.t[j], w[(base + j) % L][o], a0);
+        a1 = ffma2_s(p.fh_hi.t[j], w[(base + j) % L][o], a1);
       }
-      all[o] = a0; alh[o] = a1; ahl[o] = a2; ahh[o] = a3;
+      lo[o] = a0; hi[o] = a1;
     }
-    store2(ll_ptr, all[0], all[1], nv, false);
-    store2(hi_ptr, alh[0], alh[1], nv, true);
-    store2(hi_ptr + band, ahl[0], ahl[1], nv, true);
-    store2(hi_ptr + 2 * band, ahh[0], ahh[1], nv, true);
-    ll_ptr += llpitch;
-    hi_ptr += Wo;
+    out.row(lo[0], lo[1], hi[0], hi[1]);
   }
 }
 
-template <int L, int PW, int HSM, int XM, int V>
-__device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, const float* s0, float (&wl)[L][2],
-                                                   float (&wh)[L][2], int h0, int h_emit_end, float*& ll_ptr,
-                                                   float*& hi_ptr, long long band, int llpitch, int Wo, int nv) {
+template <int L, int PW, int HSM, int XM, int V, class Out>
+__device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, const float* s0, float2 (&w)[L][2],
+                                                   int h0, int h_emit_end, Out& out) {
   using C = AfbCfg<L, PW, HSM, XM>;
   if constexpr (V < C::UNS) {
     if (vv == V) {
       // h0 = index of this stage's first half-stage; output rows are emitted for PRO <= h < h_emit_end
-      afb_stage<L, PW, HSM, XM, C::HS * V>(p, s0, wl, wh, h0 >= C::PRO && h0 < h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage<L, PW, HSM, XM, C::HS * V>(p, s0, w, h0 >= C::PRO && h0 < h_emit_end, out);
       if constexpr (C::HS >= 2)
-        afb_stage<L, PW, HSM, XM, C::HS * V + 1>(p, s0 + 2 * C::SW, wl, wh, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end,
-                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+        afb_stage<L, PW, HSM, XM, C::HS * V + 1>(p, s0 + 2 * C::SW, w, h0 + 1 >= C::PRO && h0 + 1 < h_emit_end, out);
       if constexpr (C::HS == 4) {
-        afb_stage<L, PW, HSM, XM, C::HS * V + 2>(p, s0 + 4 * C::SW, wl, wh, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end,
-                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
-        afb_stage<L, PW, HSM, XM, C::HS * V + 3>(p, s0 + 6 * C::SW, wl, wh, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end,
-                                        ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+        afb_stage<L, PW, HSM, XM, C::HS * V + 2>(p, s0 + 4 * C::SW, w, h0 + 2 >= C::PRO && h0 + 2 < h_emit_end, out);
+        afb_stage<L, PW, HSM, XM, C::HS * V + 3>(p, s0 + 6 * C::SW, w, h0 + 3 >= C::PRO && h0 + 3 < h_emit_end, out);
       }
     } else {
-      afb_stage_dispatch<L, PW, HSM, XM, V + 1>(vv, p, s0, wl, wh, h0, h_emit_end, ll_ptr, hi_ptr, band, llpitch, Wo, nv);
+      afb_stage_dispatch<L, PW, HSM, XM, V + 1>(vv, p, s0, w, h0, h_emit_end, out);
     }
   }
 }
@@ -491,7 +559,7 @@ __device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, c
 // starting at output column k_rem (PW < 32, n_strips == 1).
 template <int L, int PW, int MINB, int HSM, int XM>
 __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
-                                                   int CH, int k_rem) {
+                                                   int CH, int k_rem, int swid) {
   using C = AfbCfg<L, PW, HSM, XM>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring
   const int lane = threadIdx.x;
@@ -505,36 +573,41 @@ __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__
   const int nplanes = imin(C::G, p.planes - plane0);
   const int plane = plane0 + g;
 
-  const int k0 = (PW == 32) ? strip * 64 : k_rem;
+  // swid = output columns per strip (even, <= 64)
+  const int k0 = (PW == 32) ? strip * swid : k_rem;
   const int ky0 = chunk * CH;
   const int ky1 = imin(ky0 + CH, p.Ho);
   const int n_half = (ky1 - ky0) + C::PRO;             // half-stages: PRO of warm-up, then one output row each
   const int n_stage = (n_half + C::HS - 1) / C::HS;
-  const int nvalid = imin(2 * PW, p.Wo - k0);
+  const int nvalid = imin((PW == 32) ? swid : 2 * PW, p.Wo - k0);
 
+  const int sh = (XM == 0 && PW == 32) ? widen_left(2 * k0 - C::HLA, C::HLA + 2 * nvalid + C::RH, p.W, p.mode,
+                                                         C::SW - 4 * C::NV - 4 * ((nvalid + 1) / 2 - 1)) : 0;
   typename C::Loader ld;
-  ld.init(ring, p.x + (long long)plane0 * p.xps, p.xps, nplanes, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA,
-          C::HLA + 2 * nvalid + C::RH, 2 * ky0 - C::PL, n_stage, lane);
+  ld.init(ring, p.x + (long long)plane0 * p.xps, p.xps, nplanes, p.H, p.W, p.xpitch, p.mode, 2 * k0 - C::HLA - sh,
+          C::HLA + 2 * nvalid + C::RH + sh, 2 * ky0 - C::PL, n_stage, lane);
   ld.prologue();
 
-  float wl[L][2], wh[L][2];
+  float2 w[L][2];
 #pragma unroll
-  for (int j = 0; j < L; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+  for (int j = 0; j < L; ++j) { w[j][0] = w[j][1] = make_float2(0.f, 0.f); }
 
-  const long long band = (long long)p.Ho * p.Wo;
-  float* ll_ptr = p.ll + (long long)plane * p.llps + (long long)ky0 * p.llpitch + k0 + 2 * jp;
-  float* hi_ptr = p.highs + (long long)plane * 3 * band + (long long)ky0 * p.Wo + k0 + 2 * jp;
-  const int nv = (g < nplanes) ? imax(0, imin(2, p.Wo - (k0 + 2 * jp))) : 0;
-  const int llpitch = p.llpitch, Wo = p.Wo;
-  const int lane_off = g * (C::RPS * C::SW) + 4 * jp;
+  DirectOut out;
+  const int hipitch = p.hipitch > 0 ? p.hipitch : p.Wo;
+  out.band = (long long)p.Ho * hipitch;
+  out.ll_ptr = p.ll + (long long)plane * p.llps + (long long)ky0 * p.llpitch + k0 + 2 * jp;
+  out.hi_ptr = p.highs + (long long)plane * 3 * out.band + (long long)ky0 * hipitch + k0 + 2 * jp;
+  out.nv = (g < nplanes) ? imax(0, imin(2, k0 + nvalid - (k0 + 2 * jp))) : 0;
+  out.llpitch = p.llpitch;
+  out.Wo = hipitch;
+  const int lane_off = g * (C::RPS * C::SW) + ((sh > 0 && out.nv == 0) ? 0 : 4 * jp + sh);
 
   int vv = 0;
 #pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    afb_stage_dispatch<L, PW, HSM, XM, 0>(vv, p, stage + lane_off, wl, wh, C::HS * t, n_half, ll_ptr, hi_ptr, band, llpitch, Wo,
-                                 nv);
+    afb_stage_dispatch<L, PW, HSM, XM, 0>(vv, p, stage + lane_off, w, C::HS * t, n_half, out);
     vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }
   cp_async_wait<0>();
@@ -544,7 +617,10 @@ template <int L, int PW, int MINB, int HSM, int XM = 0>
 inline void launch_afb_kernel(const AfbParams& p, cudaStream_t stream, long long blocks, int n_strips, int n_chunks,
                               int CH, int k_rem) {
   using C = AfbCfg<L, PW, HSM, XM>;
-  afb2d_stream<L, PW, MINB, HSM, XM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem);
+  // strips are 64 columns wide; splitting the columns evenly over the strips instead (g_tune_balanced) was
+  // measured 5 % slower (more row segments that straddle 128-byte lines)
+  const int swid = g_tune_balanced ? (p.Wo + 2 * n_strips - 1) / (2 * n_strips) * 2 : 64;
+  afb2d_stream<L, PW, MINB, HSM, XM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem, swid);
 }
 
 template <int L, int PW>

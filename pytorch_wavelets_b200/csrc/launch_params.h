@@ -50,6 +50,7 @@ inline int build_afb(AfbParams& p, const float* x, long long xps, int xpitch, fl
     return rc;
   p.x = x; p.xps = xps; p.xpitch = xpitch;
   p.ll = ll; p.llps = llps; p.llpitch = llpitch;
+  p.hipitch = 0;
   p.highs = highs;
   p.planes = planes; p.H = H; p.W = W;
   p.Ho = coeff_len(H, Lh, mode); p.Wo = coeff_len(W, Lw, mode);

@@ -94,8 +94,8 @@ def prep_filt_sfb2d(g0_col, g1_col, g0_row=None, g1_row=None, device=None):
 def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     """One analysis level on the GPU.  ``fw_*`` filter along W, ``fh_*`` along H (stored/reversed taps).
     Returns (ll (N,C,Ho,Wo), highs (N,C,3,Ho,Wo)); highs is contiguous, ll is contiguous unless ``pad_ll``:
-    then its row pitch is rounded up to 16 bytes (an internal hand-off between levels, so the next level
-    can stage it with aligned 128-bit copies)."""
+    then its row pitch is rounded up to a 128-byte line (an internal hand-off between levels: this level
+    writes it, and the next level stages it, as whole aligned lines)."""
     _ffi.require_cuda_f32(x, 'x')
     _check_bank_mode(mode)
     if x.dim() != 4:
@@ -108,7 +108,7 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     Ho = L.b200w_dwt_coeff_len(H, fh_lo.n, mode)
     Wo = L.b200w_dwt_coeff_len(W, fw_lo.n, mode)
     x, xps, xpitch = _ffi.planes_view(x)
-    Wp = (Wo + 3) // 4 * 4 if pad_ll else Wo
+    Wp = (Wo + 31) // 32 * 32 if pad_ll else Wo
     ll = x.new_empty((N, C, Ho, Wp))
     if Wp != Wo:
         ll = ll[..., :Wo]

@@ -57,8 +57,8 @@ class DWTForward(nn.Module):
         for j in range(self.J):
             # same argument order as reference transform2d.py:70-71: the *_col buffers land on the
             # Function's h*_row parameters and therefore filter along W; *_row buffers along H.
-            # Intermediate low-passes are internal hand-offs: their row pitch is padded to 16 bytes so the
-            # next level stages them with aligned copies; the returned yl is contiguous.
+            # Intermediate low-passes are internal hand-offs: their row pitch is padded to a 128-byte line so
+            # both the store and the next level's staging are line-aligned; the returned yl is contiguous.
             ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode,
                                             j < self.J - 1)
             yh.append(high)

@@ -476,3 +476,62 @@ def test_generic_and_auto_paths_agree():
     assert torch.equal(b[0], b2[0]) and all(torch.equal(p, q) for p, q in zip(b[1], b2[1]))
     ya2 = inv(a2)
     assert (ya - ya2).abs().max().item() <= 1e-5 * ya.abs().max().item()
+
+
+@pytest.mark.parametrize('mode', ['symmetric', 'reflect', 'zero', 'periodic', 'periodization'])
+@pytest.mark.parametrize('wave', ['db4', 'db2', 'db1'])
+def test_dwt_level_every_width_matches_generic(mode, wave):
+    """One analysis level for a run of widths / heights: every output-row phase inside a 128-byte line, narrow
+    last strips (one output column), single- and multi-strip planes.  The streaming kernels (per-warp stores or
+    CTA row assembly, whichever the dispatcher picks) must be bit-identical to the generic tile kernel."""
+    torch.manual_seed(29)
+    lib = _ffi.lib()
+    f = pw.DWTForward(J=1, wave=wave, mode=mode).to(DEV)
+    for W in list(range(120, 140)) + [250, 251, 252, 258, 264, 300]:
+        H = 70 + (W % 7)
+        x = torch.randn(2, 3, H, W, device=DEV)
+        try:
+            lib.b200w_debug_force_generic(1)
+            a = f(x)
+        finally:
+            lib.b200w_debug_force_generic(0)
+        b = f(x)
+        assert a[0].shape == b[0].shape
+        assert torch.equal(a[0], b[0]), (W, 'll')
+        assert torch.equal(a[1][0], b[1][0]), (W, 'highs')
+
+
+def test_dwt_row_assembly_chunked_planes_and_canaries():
+    """Few planes -> the row-assembly kernel splits planes into row chunks; the first / last partial lines of each
+    chunk must be written exactly once and nothing outside the outputs may be touched."""
+    torch.manual_seed(31)
+    lib = _ffi.lib()
+    f = pw.DWTForward(J=3, wave='db4', mode='symmetric').to(DEV)
+    x = torch.randn(1, 2, 1000, 518, device=DEV)
+    try:
+        lib.b200w_debug_force_generic(1)
+        a = f(x)
+    finally:
+        lib.b200w_debug_force_generic(0)
+    b = f(x)
+    assert torch.equal(a[0], b[0]) and all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+    # canaries around a highs buffer handed to the C ABI directly
+    from pytorch_wavelets_b200.dwt import lowlevel as ll
+    taps = [_ffi.host_taps(t) for t in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    N, C, H, W = 1, 2, 333, 518
+    x = torch.randn(N, C, H, W, device=DEV)
+    Ho, Wo = (H + 7) // 2, (W + 7) // 2
+    pad = 77
+    hbuf = torch.full((N * C * 3 * Ho * Wo + 2 * pad,), 7.5, device=DEV)
+    lbuf = torch.full((N * C * Ho * Wo + 2 * pad,), 7.5, device=DEV)
+    highs = hbuf[pad:-pad]
+    low = lbuf[pad:-pad]
+    rc = lib.b200w_dwt_afb2d(x.data_ptr(), H * W, W, low.data_ptr(), Ho * Wo, Wo, highs.data_ptr(), N * C, H, W,
+                             taps[0].ptr, taps[1].ptr, taps[0].n, taps[2].ptr, taps[3].ptr, taps[2].n,
+                             ll.mode_to_int('symmetric'), _ffi.stream_of(x))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((hbuf[:pad] == 7.5).all()) and bool((hbuf[-pad:] == 7.5).all())
+    assert bool((lbuf[:pad] == 7.5).all()) and bool((lbuf[-pad:] == 7.5).all())
+    ref_l, ref_h = ll.afb2d_level(x, f.h0_col, f.h1_col, f.h0_row, f.h1_row, ll.mode_to_int('symmetric'))
+    assert torch.equal(low.view(N, C, Ho, Wo), ref_l) and torch.equal(highs.view(N, C, 3, Ho, Wo), ref_h)
