@@ -479,12 +479,42 @@ struct AfbCfg {
 // DirectOut: straight from registers to global memory (each lane stores its two adjacent columns of each band).
 struct DirectOut {
   float* ll_ptr; float* hi_ptr; long long band; int llpitch, Wo, nv;
+  // Rows of the reference's contiguous outputs start at any 4-byte phase (Wo = 259: every other row is 8-byte
+  // misaligned).  `par` bit b = this row of plane b (0 = ll, 1..3 = the band-pass planes) is misaligned; the value is
+  // the same in every lane (lanes are 8 bytes apart), and it flips with `flip` from row to row.  One bit test per
+  // store replaces an address test + divergence bookkeeping around each of them.
+  unsigned par, flip;
+  __device__ __forceinline__ void init_parity() {
+    par = (unsigned)((reinterpret_cast<uintptr_t>(ll_ptr) >> 2) & 1) |
+          (unsigned)((reinterpret_cast<uintptr_t>(hi_ptr) >> 2) & 1) << 1 |
+          (unsigned)((reinterpret_cast<uintptr_t>(hi_ptr + band) >> 2) & 1) << 2 |
+          (unsigned)((reinterpret_cast<uintptr_t>(hi_ptr + 2 * band) >> 2) & 1) << 3;
+    flip = (unsigned)(llpitch & 1) | ((Wo & 1) ? 14u : 0u);
+  }
+  __device__ __forceinline__ void pair(float* ptr, float v0, float v1, unsigned odd, bool stream) {
+    stream = stream && (B200W_STREAM_STORES != 0);
+    if (!odd) {
+      if (stream) __stcs(reinterpret_cast<float2*>(ptr), make_float2(v0, v1));
+      else *reinterpret_cast<float2*>(ptr) = make_float2(v0, v1);
+    } else {
+      if (stream) { __stcs(ptr, v0); __stcs(ptr + 1, v1); }
+      else { ptr[0] = v0; ptr[1] = v1; }
+    }
+  }
   __device__ __forceinline__ void row(float2 lo0, float2 lo1, float2 hi0, float2 hi1) {
     // {column low-pass of (l, h)} = {ll, band 1}; {column high-pass} = {band 0, band 2}   (reference order lh, hl, hh)
-    store2(ll_ptr, lo0.x, lo1.x, nv, false);
-    store2(hi_ptr, hi0.x, hi1.x, nv, true);
-    store2(hi_ptr + band, lo0.y, lo1.y, nv, true);
-    store2(hi_ptr + 2 * band, hi0.y, hi1.y, nv, true);
+    if (nv == 2) {
+      pair(ll_ptr, lo0.x, lo1.x, par & 1u, false);
+      pair(hi_ptr, hi0.x, hi1.x, par & 2u, true);
+      pair(hi_ptr + band, lo0.y, lo1.y, par & 4u, true);
+      pair(hi_ptr + 2 * band, hi0.y, hi1.y, par & 8u, true);
+    } else if (nv == 1) {   // the last column of an odd-width plane
+      ll_ptr[0] = lo0.x;
+      hi_ptr[0] = hi0.x;
+      hi_ptr[band] = lo0.y;
+      hi_ptr[2 * band] = hi0.y;
+    }
+    par ^= flip;
     ll_ptr += llpitch;
     hi_ptr += Wo;
   }
@@ -600,6 +630,7 @@ __global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__
   out.nv = (g < nplanes) ? imax(0, imin(2, k0 + nvalid - (k0 + 2 * jp))) : 0;
   out.llpitch = p.llpitch;
   out.Wo = hipitch;
+  out.init_parity();
   const int lane_off = g * (C::RPS * C::SW) + ((sh > 0 && out.nv == 0) ? 0 : 4 * jp + sh);
 
   int vv = 0;
