@@ -61,13 +61,14 @@ struct J1Cfg {
 };
 
 template <int L0, int L1, bool SCAT, int U>
-__device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, float (&wl)[J1Cfg<L0, L1>::WR][2],
-                                         float (&wh)[J1Cfg<L0, L1>::WR][2], bool emit, float*& ll_ptr, float*& hq,
+__device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, float2 (&w)[J1Cfg<L0, L1>::WR][2],
+                                         bool emit, float*& ll_ptr, float*& hq,
                                          long long& zoff, bool colvalid, bool vec, long long zplane, long long dplane,
                                          long long ostride) {
   using C = J1Cfg<L0, L1>;
   constexpr int WR = C::WR;
-  // row pass on the two staged rows
+  // row pass on the two staged rows; window entries are {low-pass, high-pass} pairs (packed FMA where both filters
+  // have a tap on the sample, scalar FMA on the longer filter's outer taps -- same products, same order)
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float x[2 * C::NV2];
@@ -79,13 +80,17 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
     const int S = (2 * U + r) % WR;
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
-      float lo = 0.f, hi = 0.f;
+      float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < L0; ++j) lo = fmaf(p.f0.t[j], x[C::OFFX + o + (C::M - C::M0) + j], lo);
-#pragma unroll
-      for (int j = 0; j < L1; ++j) hi = fmaf(p.f1.t[j], x[C::OFFX + o + (C::M - C::M1) + j], hi);
-      wl[S][o] = lo;
-      wh[S][o] = hi;
+      for (int i = 0; i < 2 * C::M + 1; ++i) {
+        const int j0 = i - (C::M - C::M0), j1 = i - (C::M - C::M1);
+        const float xv = x[C::OFFX + o + i];
+        const bool in0 = (j0 >= 0 && j0 < L0), in1 = (j1 >= 0 && j1 < L1);
+        if (in0 && in1) acc = ffma2_s(xv, make_float2(p.f0.t[in0 ? j0 : 0], p.f1.t[in1 ? j1 : 0]), acc);
+        else if (in0) acc.x = fmaf(p.f0.t[in0 ? j0 : 0], xv, acc.x);
+        else if (in1) acc.y = fmaf(p.f1.t[in1 ? j1 : 0], xv, acc.y);
+      }
+      w[S][o] = acc;
     }
   }
   if (emit) {
@@ -94,20 +99,18 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
     for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+        float2 ac = make_float2(0.f, 0.f), bd = make_float2(0.f, 0.f);   // {ll, hl}, {lh, hh}
 #pragma unroll
         for (int j = 0; j < L0; ++j) {
           const int sl = (2 * U + dr - C::M - C::M0 + j + 4 * WR) % WR;
-          a = fmaf(p.f0.t[j], wl[sl][o], a);
-          c = fmaf(p.f0.t[j], wh[sl][o], c);
+          ac = ffma2_s(p.f0.t[j], w[sl][o], ac);
         }
 #pragma unroll
         for (int j = 0; j < L1; ++j) {
           const int sl = (2 * U + dr - C::M - C::M1 + j + 4 * WR) % WR;
-          b = fmaf(p.f1.t[j], wl[sl][o], b);
-          d = fmaf(p.f1.t[j], wh[sl][o], d);
+          bd = ffma2_s(p.f1.t[j], w[sl][o], bd);
         }
-        vll[dr][o] = a; vlh[dr][o] = b; vhl[dr][o] = c; vhh[dr][o] = d;
+        vll[dr][o] = ac.x; vlh[dr][o] = bd.x; vhl[dr][o] = ac.y; vhh[dr][o] = bd.y;
       }
     if (colvalid) {
       if (!SCAT) {
@@ -137,12 +140,12 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
 
 template <int L0, int L1, bool SCAT, int U>
 __device__ __forceinline__ void j1_dispatch(int uu, const DtParams& p, const float* s0,
-                                            float (&wl)[J1Cfg<L0, L1>::WR][2], float (&wh)[J1Cfg<L0, L1>::WR][2],
+                                            float2 (&w)[J1Cfg<L0, L1>::WR][2],
                                             bool emit, float*& ll_ptr, float*& hq, long long& zoff, bool colvalid,
                                             bool vec, long long zplane, long long dplane, long long ostride) {
   if constexpr (U < J1Cfg<L0, L1>::UNR) {
-    if (uu == U) j1_stage<L0, L1, SCAT, U>(p, s0, wl, wh, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
-    else j1_dispatch<L0, L1, SCAT, U + 1>(uu, p, s0, wl, wh, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
+    if (uu == U) j1_stage<L0, L1, SCAT, U>(p, s0, w, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
+    else j1_dispatch<L0, L1, SCAT, U + 1>(uu, p, s0, w, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
   }
 }
 
@@ -171,9 +174,9 @@ __global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtPa
           c0 - C::HLA, C::HLA + ncols + C::M, 2 * qy0 - C::M, n_stage, lane);
   ld.prologue();
 
-  float wl[C::WR][2], wh[C::WR][2];
+  float2 w[C::WR][2];
 #pragma unroll
-  for (int j = 0; j < C::WR; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+  for (int j = 0; j < C::WR; ++j) { w[j][0] = w[j][1] = make_float2(0.f, 0.f); }
 
   const bool colvalid = (c0 + 2 * lane) < p.W;
   const int h2 = p.H >> 1, w2 = p.W >> 1;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtPa
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    j1_dispatch<L0, L1, SCAT, 0>(uu, p, stage + 2 * lane, wl, wh, t >= C::PRO, ll_ptr, hq, zoff, colvalid, vec, zplane,
+    j1_dispatch<L0, L1, SCAT, 0>(uu, p, stage + 2 * lane, w, t >= C::PRO, ll_ptr, hq, zoff, colvalid, vec, zplane,
                                  dplane, ostride);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
   }
@@ -259,11 +262,15 @@ struct J2Cfg {
 };
 
 template <int MQ, int U>
-__device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, float (&wl)[2 * MQ][2],
-                                         float (&wh)[2 * MQ][2], bool emit, bool want_hi, float*& ll_ptr, float*& hq,
+__device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, float2 (&wl)[2 * MQ],
+                                         float2 (&wh)[2 * MQ], bool emit, bool want_hi, float*& ll_ptr, float*& hq,
                                          bool qvalid, bool vec) {
   using C = J2Cfg<MQ>;
   constexpr int WR = C::WR;
+  static_assert(C::OFF % 2 == 0, "sample pairs must be register pairs");
+  // Row pass: each tap multiplies the (even, odd) sample pair by a tap pair in one packed FMA.
+  //   wl[S] = {Ya(h0b), Yb(h0a)} = the low-pass interleave (a, b);  wh[S] = {Ya(h1b), Yb(h1a)} -- the high-pass
+  //   interleave is (b, a), i.e. wh[S] read back swapped.
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     float x[4 * C::NV];
@@ -272,40 +279,38 @@ __device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, flo
       const float4 v = *reinterpret_cast<const float4*>(s0 + r * C::SW + 4 * q);
       x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
-    float la = 0.f, lb = 0.f, ha = 0.f, hb = 0.f;
+    float2 l = make_float2(0.f, 0.f), h = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < MQ; ++j) {
-      const float ve = x[C::OFF + 2 * j], vo = x[C::OFF + 2 * j + 1];
-      la = fmaf(p.f2.t[j], ve, la);  // Ya with h0b
-      lb = fmaf(p.f0.t[j], vo, lb);  // Yb with h0a
-      ha = fmaf(p.f3.t[j], ve, ha);  // Ya with h1b
-      hb = fmaf(p.f1.t[j], vo, hb);  // Yb with h1a
+      const float2 xv = make_float2(x[C::OFF + 2 * j], x[C::OFF + 2 * j + 1]);
+      l = ffma2(xv, make_float2(p.f2.t[j], p.f0.t[j]), l);  // {Ya with h0b, Yb with h0a}
+      h = ffma2(xv, make_float2(p.f3.t[j], p.f1.t[j]), h);  // {Ya with h1b, Yb with h1a}
     }
     const int S = (4 * U + r) % WR;
-    wl[S][0] = la; wl[S][1] = lb;   // low-pass interleave (a, b)
-    wh[S][0] = hb; wh[S][1] = ha;   // high-pass interleave (b, a)
+    wl[S] = l;
+    wh[S] = h;
   }
   if (emit) {
     float vll[2][2], vlh[2][2], vhl[2][2], vhh[2][2];  // [half-res row 0/1][half-res col 0/1]
+    // Column pass, both half-resolution columns of a band in one packed FMA (tap broadcast).  Pairs built from wh
+    // come out column-swapped (see above).
+    float2 ll0 = make_float2(0.f, 0.f), ll1 = ll0, lh0 = ll0, lh1 = ll0, hl0 = ll0, hl1 = ll0, hh0 = ll0, hh1 = ll0;
 #pragma unroll
-    for (int dc = 0; dc < 2; ++dc) {
-      float ll0 = 0.f, ll1 = 0.f, lh0 = 0.f, lh1 = 0.f, hl0 = 0.f, hl1 = 0.f, hh0 = 0.f, hh1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < MQ; ++j) {
-        const int sa = (4 * U + 4 + 2 * j) % WR, sb = (4 * U + 5 + 2 * j) % WR;
-        const float le = wl[sa][dc], lo_ = wl[sb][dc], he = wh[sa][dc], ho = wh[sb][dc];
-        ll0 = fmaf(p.f2.t[j], le, ll0);   // ll[2q]   = Ya(h0b) on lo
-        ll1 = fmaf(p.f0.t[j], lo_, ll1);  // ll[2q+1] = Yb(h0a)
-        lh0 = fmaf(p.f1.t[j], lo_, lh0);  // lh[2q]   = Yb(h1a)   (high-pass interleave)
-        lh1 = fmaf(p.f3.t[j], le, lh1);   // lh[2q+1] = Ya(h1b)
-        hl0 = fmaf(p.f2.t[j], he, hl0);
-        hl1 = fmaf(p.f0.t[j], ho, hl1);
-        hh0 = fmaf(p.f1.t[j], ho, hh0);
-        hh1 = fmaf(p.f3.t[j], he, hh1);
-      }
-      vll[0][dc] = ll0; vll[1][dc] = ll1; vlh[0][dc] = lh0; vlh[1][dc] = lh1;
-      vhl[0][dc] = hl0; vhl[1][dc] = hl1; vhh[0][dc] = hh0; vhh[1][dc] = hh1;
+    for (int j = 0; j < MQ; ++j) {
+      const int sa = (4 * U + 4 + 2 * j) % WR, sb = (4 * U + 5 + 2 * j) % WR;
+      ll0 = ffma2_s(p.f2.t[j], wl[sa], ll0);   // ll[2q]   = Ya(h0b) on lo
+      ll1 = ffma2_s(p.f0.t[j], wl[sb], ll1);   // ll[2q+1] = Yb(h0a)
+      lh0 = ffma2_s(p.f1.t[j], wl[sb], lh0);   // lh[2q]   = Yb(h1a)   (high-pass interleave)
+      lh1 = ffma2_s(p.f3.t[j], wl[sa], lh1);   // lh[2q+1] = Ya(h1b)
+      hl0 = ffma2_s(p.f2.t[j], wh[sa], hl0);
+      hl1 = ffma2_s(p.f0.t[j], wh[sb], hl1);
+      hh0 = ffma2_s(p.f1.t[j], wh[sb], hh0);
+      hh1 = ffma2_s(p.f3.t[j], wh[sa], hh1);
     }
+    vll[0][0] = ll0.x; vll[0][1] = ll0.y; vll[1][0] = ll1.x; vll[1][1] = ll1.y;
+    vlh[0][0] = lh0.x; vlh[0][1] = lh0.y; vlh[1][0] = lh1.x; vlh[1][1] = lh1.y;
+    vhl[0][0] = hl0.y; vhl[0][1] = hl0.x; vhl[1][0] = hl1.y; vhl[1][1] = hl1.x;
+    vhh[0][0] = hh0.y; vhh[0][1] = hh0.x; vhh[1][0] = hh1.y; vhh[1][1] = hh1.x;
     if (qvalid) {
       store2(ll_ptr, vll[0][0], vll[0][1], 2, false);
       store2(ll_ptr + p.outpitch, vll[1][0], vll[1][1], 2, false);
@@ -322,8 +327,8 @@ __device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, flo
 }
 
 template <int MQ, int U>
-__device__ __forceinline__ void j2_dispatch(int uu, const DtParams& p, const float* s0, float (&wl)[2 * MQ][2],
-                                            float (&wh)[2 * MQ][2], bool emit, bool want_hi, float*& ll_ptr,
+__device__ __forceinline__ void j2_dispatch(int uu, const DtParams& p, const float* s0, float2 (&wl)[2 * MQ],
+                                            float2 (&wh)[2 * MQ], bool emit, bool want_hi, float*& ll_ptr,
                                             float*& hq, bool qvalid, bool vec) {
   if constexpr (U < J2Cfg<MQ>::UNR) {
     if (uu == U) j2_stage<MQ, U>(p, s0, wl, wh, emit, want_hi, ll_ptr, hq, qvalid, vec);
@@ -356,9 +361,9 @@ __global__ void __launch_bounds__(32) fwd_j2plus_stream(const __grid_constant__ 
           C::HLA + 4 * nq + C::HL, 4 * qy0 + 2 - MQ, n_stage, lane);
   ld.prologue();
 
-  float wl[C::WR][2], wh[C::WR][2];
+  float2 wl[C::WR], wh[C::WR];
 #pragma unroll
-  for (int j = 0; j < C::WR; ++j) { wl[j][0] = wl[j][1] = wh[j][0] = wh[j][1] = 0.f; }
+  for (int j = 0; j < C::WR; ++j) { wl[j] = wh[j] = make_float2(0.f, 0.f); }
 
   const bool qvalid = (q0 + lane) < Q;
   const bool want_hi = (p.highs != nullptr);
