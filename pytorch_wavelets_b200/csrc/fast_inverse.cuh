@@ -22,10 +22,12 @@ struct SfbCfg {
   static_assert(HALF - 1 <= 32, "halo must fit the third 32-lane copy");
 };
 
-// one coefficient row: W pass into window slot U, then (if emit) the H pass for the output row pair
+// one coefficient row: W pass into window slot U, then (if emit) the H pass for the output row pair.
+// Packed FMA throughout: along W a coefficient times the (even, odd)-phase tap pair gives both output columns it
+// feeds; along H a tap times a window column pair gives two adjacent outputs of one row.
 template <int L, int U>
-__device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, float (&wP)[L / 2][4],
-                                        float (&wQ)[L / 2][4], bool emit, float*& y_ptr, int ypitch, int nv4,
+__device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, float2 (&wP)[L / 2][2],
+                                        float2 (&wQ)[L / 2][2], bool emit, float*& y_ptr, int ypitch, int nv4,
                                         bool row1_ok, bool vec4) {
   using C = SfbCfg<L>;
   constexpr int HALF = C::HALF;
@@ -39,46 +41,46 @@ __device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, f
     }
   // W pass: P = S(ll; gw_lo) + S(hl; gw_hi), Q = S(lh; gw_lo) + S(hh; gw_hi)   (bands: 0 ll, 1 lh, 2 hl, 3 hh)
 #pragma unroll
-  for (int e = 0; e < 2; ++e)
+  for (int e = 0; e < 2; ++e) {
+    float2 s_ll = make_float2(0.f, 0.f), s_lh = s_ll, s_hl = s_ll, s_hh = s_ll;   // {phase 0, phase 1}
 #pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-      float s_ll = 0.f, s_lh = 0.f, s_hl = 0.f, s_hh = 0.f;
-#pragma unroll
-      for (int i = 0; i < HALF; ++i) {
-        const float g0 = p.gw_lo.t[L - 2 - 2 * i + ph], g1 = p.gw_hi.t[L - 2 - 2 * i + ph];
-        s_ll = fmaf(a[0][e + i], g0, s_ll);
-        s_lh = fmaf(a[1][e + i], g0, s_lh);
-        s_hl = fmaf(a[2][e + i], g1, s_hl);
-        s_hh = fmaf(a[3][e + i], g1, s_hh);
-      }
-      wP[U][2 * e + ph] = __fadd_rn(s_ll, s_hl);
-      wQ[U][2 * e + ph] = __fadd_rn(s_lh, s_hh);
+    for (int i = 0; i < HALF; ++i) {
+      const float2 g0 = make_float2(p.gw_lo.t[L - 2 - 2 * i], p.gw_lo.t[L - 1 - 2 * i]);
+      const float2 g1 = make_float2(p.gw_hi.t[L - 2 - 2 * i], p.gw_hi.t[L - 1 - 2 * i]);
+      s_ll = ffma2_s(a[0][e + i], g0, s_ll);
+      s_lh = ffma2_s(a[1][e + i], g0, s_lh);
+      s_hl = ffma2_s(a[2][e + i], g1, s_hl);
+      s_hh = ffma2_s(a[3][e + i], g1, s_hh);
     }
+    wP[U][e] = make_float2(__fadd_rn(s_ll.x, s_hl.x), __fadd_rn(s_ll.y, s_hl.y));
+    wQ[U][e] = make_float2(__fadd_rn(s_lh.x, s_hh.x), __fadd_rn(s_lh.y, s_hh.y));
+  }
   if (emit) {
-    float o[2][4];
+    float2 o[2][2];  // [output row of the pair][column pair]
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float s0 = 0.f, s1 = 0.f;
+      for (int e = 0; e < 2; ++e) {
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
 #pragma unroll
         for (int i = 0; i < HALF; ++i) {
           const int sl = (U + 1 + i) % HALF;
-          s0 = fmaf(wP[sl][c], p.gh_lo.t[L - 2 - 2 * i + ph], s0);
-          s1 = fmaf(wQ[sl][c], p.gh_hi.t[L - 2 - 2 * i + ph], s1);
+          s0 = ffma2_s(p.gh_lo.t[L - 2 - 2 * i + ph], wP[sl][e], s0);
+          s1 = ffma2_s(p.gh_hi.t[L - 2 - 2 * i + ph], wQ[sl][e], s1);
         }
-        o[ph][c] = __fadd_rn(s0, s1);
+        o[ph][e] = make_float2(__fadd_rn(s0.x, s1.x), __fadd_rn(s0.y, s1.y));
       }
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph) {
       if (ph == 1 && !row1_ok) break;
       float* q = y_ptr + ph * ypitch;
       if (vec4 && nv4 == 4) {
-        *reinterpret_cast<float4*>(q) = make_float4(o[ph][0], o[ph][1], o[ph][2], o[ph][3]);
+        *reinterpret_cast<float4*>(q) = make_float4(o[ph][0].x, o[ph][0].y, o[ph][1].x, o[ph][1].y);
       } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nv4) q[c] = o[ph][c];
+        if (0 < nv4) q[0] = o[ph][0].x;
+        if (1 < nv4) q[1] = o[ph][0].y;
+        if (2 < nv4) q[2] = o[ph][1].x;
+        if (3 < nv4) q[3] = o[ph][1].y;
       }
     }
     y_ptr += 2 * ypitch;
@@ -87,7 +89,7 @@ __device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, f
 
 template <int L, int V>
 __device__ __forceinline__ void sfb_stage_dispatch(int vv, const SfbParams& p, const float* stage,
-                                                   float (&wP)[L / 2][4], float (&wQ)[L / 2][4], int rho0,
+                                                   float2 (&wP)[L / 2][2], float2 (&wQ)[L / 2][2], int rho0,
                                                    int rho_end, int m0, float*& y_ptr, int ypitch, int nv4, bool vec4) {
   using C = SfbCfg<L>;
   if constexpr (V < C::UNS) {
@@ -147,9 +149,13 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
   const bool ok1 = (c0 + 32 + lane) < p.Wc;
   const bool ok2 = (lane < C::HALF - 1) && ((c0 + 64 + lane) < p.Wc);
 
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + 4 * lane;
+  int slot_i = 0;
   auto issue = [&](int t) {
+    const int slot = slot_i;
+    slot_i = (slot_i + 1 == C::NS) ? 0 : slot_i + 1;
     if (t < n_stage) {
-      float* dst = ring + (t % C::NS) * C::STAGE;
+      const unsigned dst = ring_s + slot * (C::STAGE * 4);
 #pragma unroll
       for (int r = 0; r < C::KR; ++r) {
         const int k = m0 + C::KR * t + r;
@@ -157,11 +163,11 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             if (bptr[b] == nullptr) continue;
-            const float* src = bptr[b] + (long long)k * bpitch[b];
-            float* d = dst + (r * 4 + b) * C::SWB;
-            if (ok0) cp_async4(d + lane, src + lane);
-            if (ok1) cp_async4(d + 32 + lane, src + 32 + lane);
-            if (ok2) cp_async4(d + 64 + lane, src + 64 + lane);
+            const float* src = bptr[b] + (long long)k * bpitch[b] + lane;
+            const unsigned d = dst + (r * 4 + b) * (C::SWB * 4);
+            if (ok0) cp_async4_s(d, src);
+            if (ok1) cp_async4_s(d + 128, src + 32);
+            if (ok2) cp_async4_s(d + 256, src + 64);
           }
         }
       }
@@ -171,24 +177,25 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
 #pragma unroll 1
   for (int t = 0; t < C::NS - 1; ++t) issue(t);
 
-  float wP[C::HALF][4], wQ[C::HALF][4];
+  float2 wP[C::HALF][2], wQ[C::HALF][2];
 #pragma unroll
   for (int j = 0; j < C::HALF; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { wP[j][c] = 0.f; wQ[j][c] = 0.f; }
+    for (int c = 0; c < 2; ++c) { wP[j][c] = make_float2(0.f, 0.f); wQ[j][c] = make_float2(0.f, 0.f); }
 
   const int col0 = 2 * c0 + 4 * lane;
   float* y_ptr = p.y + (long long)plane * p.yps + (long long)(2 * m0) * p.ypitch + col0;
   const int nv4 = imax(0, imin(4, p.Wo - col0));
   const bool vec4 = ((p.ypitch & 3) == 0) && ((p.yps & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
 
-  int vv = 0;
+  int vv = 0, slot_a = 0;
 #pragma unroll 1
   for (int t = 0; t < n_stage; ++t) {
     cp_async_wait<C::NS - 2>();
     __syncwarp();
     issue(t + C::NS - 1);
-    const float* stage = ring + (t % C::NS) * C::STAGE + 2 * lane;
+    const float* stage = ring + slot_a * C::STAGE + 2 * lane;
+    slot_a = (slot_a + 1 == C::NS) ? 0 : slot_a + 1;
     sfb_stage_dispatch<L, 0>(vv, p, stage, wP, wQ, C::KR * t, n_rows, m0, y_ptr, p.ypitch, nv4, vec4);
     vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }

@@ -61,6 +61,9 @@ __device__ __forceinline__ void cp_async16_s(unsigned s, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async4_s(unsigned s, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ float lds_s(unsigned s) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(s) : "memory");
