@@ -469,7 +469,10 @@ struct AfbCfg {
   static constexpr int HS0 = ((L / 2) % 4 == 0) ? 4 : (((L / 2) % 2 == 0) ? 2 : 1);
   static constexpr int HS = (HS0 < HSM) ? HS0 : HSM;
   static constexpr int RPS = 2 * HS;                 // image rows per stage
-  static constexpr int NS = (HS == 4) ? 2 : ((HS == 2) ? 3 : 4);  // ring depth in stages (4 with HS == 2 measured slower)
+#ifndef B200W_AFB_NS
+#define B200W_AFB_NS 3
+#endif
+  static constexpr int NS = (HS == 4) ? 2 : ((HS == 2) ? B200W_AFB_NS : 4);  // ring depth in stages
   static constexpr int NFIX = (PW == 32) ? (RPS * 2 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage
   static constexpr int SMEM_BYTES = (NS * RPS * G * SW + 2 * NS) * 4;
   static constexpr int PRO = (L - 2) / 2;            // prologue half-stages before the first output row
