@@ -39,7 +39,7 @@ def needs_build():
 
 def build(force=False, verbose=False, out=None, extra_flags=()):
     """Compile the library.  ``out`` / ``extra_flags`` build an experimental variant next to the default one
-    (tools/variants.py); the package itself only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
+    (see profiles/r01_notes.md, "A/B discipline"); the package itself only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
     target = out or SO
     if out is None and not force and not needs_build():
         return SO

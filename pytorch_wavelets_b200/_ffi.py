@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200W_LIB: load an experimental build of the same library instead (tools/variants.py); still CUDA-only.
+# B200W_LIB: load an experimental build of the same library instead (see profiles/r01_notes.md, "A/B discipline"); still CUDA-only.
 SO_PATH = os.environ.get('B200W_LIB') or os.path.join(_HERE, 'libb200wave.so')
 _lib = None
 

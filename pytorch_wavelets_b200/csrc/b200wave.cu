@@ -176,9 +176,7 @@ int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr, int N,
  * where a specialisation exists, generic tile kernels otherwise), 1 = force the generic tile kernels.
  * Testing / benchmarking aid; process-wide. */
 void b200w_debug_force_generic(int on) { fast::g_force_generic = on; }
-/* tuning knob for experiments: register cap of the DWT streaming kernel (0 = compiler default, 24, 32) */
-void b200w_debug_set_minb(int v) { fast::g_tune_minb = v; }
-void b200w_debug_set_hs(int v) { fast::g_tune_hs = v; }
+/* knobs of the measurement probes (tools/align_probe.py, tools/pitch_probe.py, tools/quick_fwd.py) */
 void b200w_debug_set_want(int v) { fast::g_tune_want = v; }
 void b200w_debug_set_hipitch(int v) { fast::g_tune_hipitch = v; }
 void b200w_debug_set_balanced(int v) { fast::g_tune_balanced = v; }

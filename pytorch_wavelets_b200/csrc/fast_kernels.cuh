@@ -27,13 +27,11 @@ namespace fast {
 
 constexpr int kNoFastPath = 1;
 static int g_force_generic = 0;
-static int g_tune_minb = 0;
-static int g_tune_hs = 0;
 static long long g_tune_want = 0;
 static int g_tune_hipitch = 0;
 static int g_tune_balanced = 0;
 
-// experiment switches (see tools/variants.py): L2 prefetch qualifier of the staging copies, streaming stores
+// experiment switches (-D at build time, see _build.build(extra_flags=...)): L2 prefetch qualifier of the staging copies, streaming stores
 #ifndef B200W_CPASYNC_L2
 #define B200W_CPASYNC_L2 0
 #endif
@@ -678,15 +676,9 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
     launch_afb_kernel<L, PW, 1, 2, 1>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
     return 0;
   }
-  // tuning knobs (experiments): register cap MINB and rows per stage (HSM half-stages)
-  if (g_tune_hs == 4) {
-    launch_afb_kernel<L, PW, 1, 4>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-  } else {
-    // register caps (__launch_bounds__(32, 18..32)) were measured: they speed the small levels up a little but cost
-    // 15 % on the large one, so the default is the uncapped allocation
-    if (g_tune_minb == 20 && L <= 8) launch_afb_kernel<L, PW, 20, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-    else launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
-  }
+  // measured and not kept: register caps (__launch_bounds__(32, 18..32): a little faster on the small levels, 15 % slower
+  // on the large one) and 8-row stages (1.97 vs 1.91 ms) -- profiles/r01_notes.md
+  launch_afb_kernel<L, PW, 1, 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   return 0;
 }
 

@@ -3,9 +3,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pytorch_wavelets_b200 as pw
 from pytorch_wavelets_b200 import _ffi
-import ctypes
-if os.environ.get('MINB'):
-    _ffi.lib().b200w_debug_set_minb.argtypes = [ctypes.c_int]; _ffi.lib().b200w_debug_set_minb(int(os.environ['MINB']))
 x = torch.randn(128, 32, 512, 512, device='cuda'); f = pw.DWTForward(J=3, wave='db4', mode='symmetric').cuda()
 with torch.no_grad():
     for _ in range(3): f(x)
@@ -14,4 +11,4 @@ with torch.no_grad():
     with rec:
         for _ in range(10): f(x)
     s = rec.summary()
-print(os.path.basename(_ffi.SO_PATH), 'MINB', os.environ.get('MINB'), {k.split()[1]: round(v['avg_ms'], 4) for k, v in sorted(s.items())})
+print(os.path.basename(_ffi.SO_PATH), {k.split()[1]: round(v['avg_ms'], 4) for k, v in sorted(s.items())})
