@@ -267,8 +267,8 @@ struct I1Cfg {
 
 template <int L0, int L1, int U>
 __device__ __forceinline__ void i1_stage(const DtParams& p, const float* band, const float* llrow, bool has_hi,
-                                         bool has_ll, float (&wA)[I1Cfg<L0, L1>::WR][2],
-                                         float (&wB)[I1Cfg<L0, L1>::WR][2], bool emit, float*& y_ptr, bool colvalid) {
+                                         bool has_ll, float2 (&wA)[I1Cfg<L0, L1>::WR],
+                                         float2 (&wB)[I1Cfg<L0, L1>::WR], bool emit, float*& y_ptr, bool colvalid) {
   using C = I1Cfg<L0, L1>;
   constexpr int WR = C::WR;
 #pragma unroll
@@ -286,6 +286,7 @@ __device__ __forceinline__ void i1_stage(const DtParams& p, const float* band, c
       xll[2 * q] = d.x; xll[2 * q + 1] = d.y;
     }
     const int S = (2 * U + rr) % WR;
+    float a2[2], b2[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       float r1hh = 0.f, r1hl = 0.f, r0lh = 0.f, r0ll = 0.f;
@@ -302,24 +303,23 @@ __device__ __forceinline__ void i1_stage(const DtParams& p, const float* band, c
         r0ll = fmaf(p.f0.t[j], xll[ix], r0ll);
       }
       // A = R1(hh) + R0(lh);  B = R1(hl) + R0(ll)   (absent inputs contribute exact zeros)
-      wA[S][e] = has_hi ? __fadd_rn(r1hh, r0lh) : 0.f;
-      wB[S][e] = has_hi ? (has_ll ? __fadd_rn(r1hl, r0ll) : r1hl) : r0ll;
+      a2[e] = has_hi ? __fadd_rn(r1hh, r0lh) : 0.f;
+      b2[e] = has_hi ? (has_ll ? __fadd_rn(r1hl, r0ll) : r1hl) : r0ll;
     }
+    wA[S] = make_float2(a2[0], a2[1]);
+    wB[S] = make_float2(b2[0], b2[1]);
   }
   if (emit) {
+    // column pass: one packed FMA per tap covers the lane's two output columns
 #pragma unroll
     for (int dr = 0; dr < 2; ++dr) {
-      float o[2];
+      float2 a = make_float2(0.f, 0.f), b = a;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float a = 0.f, b = 0.f;
+      for (int j = 0; j < L1; ++j) a = ffma2_s(p.f1.t[j], wA[(2 * U - 2 * C::MS + dr - C::M1 + j + 4 * WR) % WR], a);
 #pragma unroll
-        for (int j = 0; j < L1; ++j) a = fmaf(p.f1.t[j], wA[(2 * U - 2 * C::MS + dr - C::M1 + j + 4 * WR) % WR][e], a);
-#pragma unroll
-        for (int j = 0; j < L0; ++j) b = fmaf(p.f0.t[j], wB[(2 * U - 2 * C::MS + dr - C::M0 + j + 4 * WR) % WR][e], b);
-        o[e] = has_hi ? __fadd_rn(a, b) : b;
-      }
-      if (colvalid) store2(y_ptr + dr * p.outpitch, o[0], o[1], 2, false);
+      for (int j = 0; j < L0; ++j) b = ffma2_s(p.f0.t[j], wB[(2 * U - 2 * C::MS + dr - C::M0 + j + 4 * WR) % WR], b);
+      const float o0 = has_hi ? __fadd_rn(a.x, b.x) : b.x, o1 = has_hi ? __fadd_rn(a.y, b.y) : b.y;
+      if (colvalid) store2(y_ptr + dr * p.outpitch, o0, o1, 2, false);
     }
     y_ptr += 2 * p.outpitch;
   }
@@ -327,8 +327,8 @@ __device__ __forceinline__ void i1_stage(const DtParams& p, const float* band, c
 
 template <int L0, int L1, int U>
 __device__ __forceinline__ void i1_dispatch(int uu, const DtParams& p, const float* band, const float* llrow,
-                                            bool has_hi, bool has_ll, float (&wA)[I1Cfg<L0, L1>::WR][2],
-                                            float (&wB)[I1Cfg<L0, L1>::WR][2], bool emit, float*& y_ptr,
+                                            bool has_hi, bool has_ll, float2 (&wA)[I1Cfg<L0, L1>::WR],
+                                            float2 (&wB)[I1Cfg<L0, L1>::WR], bool emit, float*& y_ptr,
                                             bool colvalid) {
   if constexpr (U < I1Cfg<L0, L1>::UNR) {
     if (uu == U) i1_stage<L0, L1, U>(p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid);
@@ -540,9 +540,9 @@ __global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtPa
   qs.init(smem, p, plane, c0, C::HLA + ncols + C::M, i0, n_stage, lane);
   qs.prologue();
 
-  float wA[C::WR][2], wB[C::WR][2];
+  float2 wA[C::WR], wB[C::WR];
 #pragma unroll
-  for (int j = 0; j < C::WR; ++j) { wA[j][0] = wA[j][1] = wB[j][0] = wB[j][1] = 0.f; }
+  for (int j = 0; j < C::WR; ++j) { wA[j] = wB[j] = make_float2(0.f, 0.f); }
 
   const bool colvalid = (c0 + 2 * lane) < p.W;
   float* y_ptr = p.out + (long long)plane * p.outps + (long long)(2 * i0) * p.outpitch + c0 + 2 * lane;
@@ -625,7 +625,7 @@ struct I2Cfg {
 
 template <int MQ, int U>
 __device__ __forceinline__ void i2_stage(const DtParams& p, const float* band, const float* llrow, bool has_hi,
-                                         bool has_ll, float (&wA)[I2Cfg<MQ>::WR][4], float (&wB)[I2Cfg<MQ>::WR][4],
+                                         bool has_ll, float2 (&wA)[I2Cfg<MQ>::WR][2], float2 (&wB)[I2Cfg<MQ>::WR][2],
                                          bool emit, float*& y_ptr, bool colvalid, bool vec4) {
   using C = I2Cfg<MQ>;
   using PL = IfPhase<C::M2, false>;
@@ -646,6 +646,7 @@ __device__ __forceinline__ void i2_stage(const DtParams& p, const float* band, c
       xll[2 * q] = d.x; xll[2 * q + 1] = d.y;
     }
     const int S = (2 * U + rr) % WR;
+    float a4[4], b4[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       // s even -> ha, s odd -> hb;  low: ha=g0b(f2) hb=g0a(f0);  high: ha=g1b(f3) hb=g1a(f1)
@@ -662,32 +663,34 @@ __device__ __forceinline__ void i2_stage(const DtParams& p, const float* band, c
         rl_lh = fmaf(cl, xlh[il], rl_lh);
         rl_ll = fmaf(cl, xll[il], rl_ll);
       }
-      wA[S][s] = has_hi ? __fadd_rn(rh_hh, rl_lh) : 0.f;
-      wB[S][s] = has_hi ? (has_ll ? __fadd_rn(rh_hl, rl_ll) : rh_hl) : rl_ll;
+      a4[s] = has_hi ? __fadd_rn(rh_hh, rl_lh) : 0.f;
+      b4[s] = has_hi ? (has_ll ? __fadd_rn(rh_hl, rl_ll) : rh_hl) : rl_ll;
     }
+    wA[S][0] = make_float2(a4[0], a4[1]); wA[S][1] = make_float2(a4[2], a4[3]);
+    wB[S][0] = make_float2(b4[0], b4[1]); wB[S][1] = make_float2(b4[2], b4[3]);
   }
   if (emit) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {   // output row 4i + s
+    for (int s = 0; s < 4; ++s) {   // output row 4i + s; one packed FMA per tap covers two of the lane's four columns
       const float* fl = (s & 1) ? p.f0.t : p.f2.t;
       const float* fh = (s & 1) ? p.f1.t : p.f3.t;
-      float o[4];
+      float2 o[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float a = 0.f, b = 0.f;
+      for (int c = 0; c < 2; ++c) {
+        float2 a = make_float2(0.f, 0.f), b = a;
 #pragma unroll
         for (int j = 0; j < M2; ++j) {
           const int sh = (2 * U - 2 * C::MS + 2 * j + PH::off(s) - M2 + 4 * WR) % WR;
           const int sl = (2 * U - 2 * C::MS + 2 * j + PL::off(s) - M2 + 4 * WR) % WR;
-          a = fmaf(fh[2 * j + PH::par(s)], wA[sh][c], a);
-          b = fmaf(fl[2 * j + PL::par(s)], wB[sl][c], b);
+          a = ffma2_s(fh[2 * j + PH::par(s)], wA[sh][c], a);
+          b = ffma2_s(fl[2 * j + PL::par(s)], wB[sl][c], b);
         }
-        o[c] = has_hi ? __fadd_rn(a, b) : b;
+        o[c] = has_hi ? make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)) : b;
       }
       if (colvalid) {
         float* q = y_ptr + s * p.outpitch;
-        if (vec4) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
-        else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; q[3] = o[3]; }
+        if (vec4) *reinterpret_cast<float4*>(q) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        else { q[0] = o[0].x; q[1] = o[0].y; q[2] = o[1].x; q[3] = o[1].y; }
       }
     }
     y_ptr += 4 * p.outpitch;
@@ -696,8 +699,8 @@ __device__ __forceinline__ void i2_stage(const DtParams& p, const float* band, c
 
 template <int MQ, int U>
 __device__ __forceinline__ void i2_dispatch(int uu, const DtParams& p, const float* band, const float* llrow,
-                                            bool has_hi, bool has_ll, float (&wA)[I2Cfg<MQ>::WR][4],
-                                            float (&wB)[I2Cfg<MQ>::WR][4], bool emit, float*& y_ptr, bool colvalid,
+                                            bool has_hi, bool has_ll, float2 (&wA)[I2Cfg<MQ>::WR][2],
+                                            float2 (&wB)[I2Cfg<MQ>::WR][2], bool emit, float*& y_ptr, bool colvalid,
                                             bool vec4) {
   if constexpr (U < I2Cfg<MQ>::UNR) {
     if (uu == U) i2_stage<MQ, U>(p, band, llrow, has_hi, has_ll, wA, wB, emit, y_ptr, colvalid, vec4);
@@ -728,11 +731,11 @@ __global__ void __launch_bounds__(32) inv_j2plus_stream(const __grid_constant__ 
   qs.init(smem, p, plane, c0, C::HLA + ncols + C::HR, i0, n_stage, lane);
   qs.prologue();
 
-  float wA[C::WR][4], wB[C::WR][4];
+  float2 wA[C::WR][2], wB[C::WR][2];
 #pragma unroll
   for (int j = 0; j < C::WR; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { wA[j][c] = 0.f; wB[j][c] = 0.f; }
+    for (int c = 0; c < 2; ++c) { wA[j][c] = make_float2(0.f, 0.f); wB[j][c] = make_float2(0.f, 0.f); }
 
   const bool colvalid = (c0 + 2 * lane) < p.W;
   float* y_ptr = p.out + (long long)plane * p.outps + (long long)(4 * i0) * p.outpitch + 2 * c0 + 4 * lane;
