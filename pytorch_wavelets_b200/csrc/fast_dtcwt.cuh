@@ -233,6 +233,11 @@ inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
   if (p.L0 == 9 && p.L1 == 7) return launch_j1_stream<9, 7, SCAT>(p, stream);   // antonini
   if (p.L0 == 5 && p.L1 == 3) return launch_j1_stream<5, 3, SCAT>(p, stream);   // legall
   if (p.L0 == 13 && p.L1 == 19) return launch_j1_stream<13, 19, SCAT>(p, stream);  // near_sym_b
+  if (!SCAT) {  // synthesis filter pairs: the backward pass of the level-1 inverse
+    if (p.L0 == 7 && p.L1 == 9) return launch_j1_stream<7, 9, false>(p, stream);    // antonini
+    if (p.L0 == 3 && p.L1 == 5) return launch_j1_stream<3, 5, false>(p, stream);    // legall
+    if (p.L0 == 19 && p.L1 == 13) return launch_j1_stream<19, 13, false>(p, stream);  // near_sym_b
+  }
   return kNoFastPath;
 }
 inline int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<false>(p, stream); }
@@ -408,5 +413,8 @@ inline int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream) {
   if (g_force_generic) return kNoFastPath;
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 10) return launch_j2_stream<10>(p, stream);  // qshift_a, qshift_06
+  if (p.L0 == 14) return launch_j2_stream<14>(p, stream);  // qshift_b
+  if (p.L0 == 16) return launch_j2_stream<16>(p, stream);  // qshift_c
+  if (p.L0 == 18) return launch_j2_stream<18>(p, stream);  // qshift_d
   return kNoFastPath;
 }

@@ -581,6 +581,12 @@ inline int try_launch_inv_j1(const DtParams& p, cudaStream_t stream) {
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 7 && p.L1 == 5) return launch_i1_stream<7, 5>(p, stream);   // near_sym_a synthesis
   if (p.L0 == 5 && p.L1 == 7) return launch_i1_stream<5, 7>(p, stream);   // near_sym_a analysis (backward of fwd)
+  if (p.L0 == 7 && p.L1 == 9) return launch_i1_stream<7, 9>(p, stream);   // antonini synthesis
+  if (p.L0 == 3 && p.L1 == 5) return launch_i1_stream<3, 5>(p, stream);   // legall synthesis
+  if (p.L0 == 19 && p.L1 == 13) return launch_i1_stream<19, 13>(p, stream);  // near_sym_b synthesis
+  if (p.L0 == 9 && p.L1 == 7) return launch_i1_stream<9, 7>(p, stream);   // antonini analysis (backward of fwd)
+  if (p.L0 == 5 && p.L1 == 3) return launch_i1_stream<5, 3>(p, stream);   // legall analysis
+  if (p.L0 == 13 && p.L1 == 19) return launch_i1_stream<13, 19>(p, stream);  // near_sym_b analysis
   return kNoFastPath;
 }
 
@@ -774,5 +780,8 @@ inline int try_launch_inv_j2plus(const DtParams& p, cudaStream_t stream) {
   if (g_force_generic) return kNoFastPath;
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 10) return launch_i2_stream<10>(p, stream);  // qshift_a, qshift_06
+  if (p.L0 == 14) return launch_i2_stream<14>(p, stream);  // qshift_b
+  if (p.L0 == 16) return launch_i2_stream<16>(p, stream);  // qshift_c
+  if (p.L0 == 18) return launch_i2_stream<18>(p, stream);  // qshift_d
   return kNoFastPath;
 }

@@ -342,10 +342,14 @@ def test_dwt_gradient_identities(wave, J, mode):
         assert (a.grad - b).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('biort,qshift', [('near_sym_a', 'qshift_a'), ('near_sym_b', 'qshift_b'),
+                                          ('antonini', 'qshift_c'), ('legall', 'qshift_d')])
 @pytest.mark.parametrize('o_dim,ri_dim', [(2, -1), (1, 2)])
-def test_dtcwt_backward_is_adjoint(o_dim, ri_dim):
+def test_dtcwt_backward_is_adjoint(o_dim, ri_dim, biort, qshift):
+    """Backward passes run the opposite transform's kernels with the stored filters (every filter pair has its own
+    streaming instantiation for the default layout; other layouts take the generic kernels)."""
     torch.manual_seed(9)
-    f = pw.DTCWTForward(J=3, o_dim=o_dim, ri_dim=ri_dim).to(DEV)
+    f = pw.DTCWTForward(J=3, o_dim=o_dim, ri_dim=ri_dim, biort=biort, qshift=qshift).to(DEV)
     x = torch.randn(2, 2, 64, 96, device=DEV, requires_grad=True)
     yl, yh = f(x)
     outs = [yl] + yh
@@ -357,7 +361,7 @@ def test_dtcwt_backward_is_adjoint(o_dim, ri_dim):
     lhs = _flat_dot([yl2] + yh2, ws)
     rhs = _dot(x2, x.grad)
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
-    i = pw.DTCWTInverse(o_dim=o_dim, ri_dim=ri_dim).to(DEV)
+    i = pw.DTCWTInverse(o_dim=o_dim, ri_dim=ri_dim, biort=biort, qshift=qshift).to(DEV)
     cl = yl.detach().clone().requires_grad_(True)
     ch = [h.detach().clone().requires_grad_(True) for h in yh]
     y = i((cl, ch))
