@@ -227,7 +227,10 @@ inline int try_launch_sfb(const SfbParams& p, cudaStream_t stream) {
     case 8: return launch_sfb_stream<8>(p, stream);
     case 10: return launch_sfb_stream<10>(p, stream);
     case 12: return launch_sfb_stream<12>(p, stream);
+    case 14: return launch_sfb_stream<14>(p, stream);
     case 16: return launch_sfb_stream<16>(p, stream);
+    case 18: return launch_sfb_stream<18>(p, stream);
+    case 20: return launch_sfb_stream<20>(p, stream);
     default: return kNoFastPath;
   }
 }

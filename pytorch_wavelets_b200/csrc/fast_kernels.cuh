@@ -705,7 +705,10 @@ inline int try_launch_afb(const AfbParams& p, cudaStream_t stream) {
     case 8: return launch_afb_stream<8>(p, stream);
     case 10: return launch_afb_stream<10>(p, stream);
     case 12: return launch_afb_stream<12>(p, stream);
+    case 14: return launch_afb_stream<14>(p, stream);
     case 16: return launch_afb_stream<16>(p, stream);
+    case 18: return launch_afb_stream<18>(p, stream);
+    case 20: return launch_afb_stream<20>(p, stream);
     default: return kNoFastPath;
   }
 }
