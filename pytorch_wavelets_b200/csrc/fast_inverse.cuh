@@ -25,10 +25,13 @@ struct SfbCfg {
 // one coefficient row: W pass into window slot U, then (if emit) the H pass for the output row pair.
 // Packed FMA throughout: along W a coefficient times the (even, odd)-phase tap pair gives both output columns it
 // feeds; along H a tap times a window column pair gives two adjacent outputs of one row.
-template <int L, int U>
+// PER (periodization): the same sums over the periodic extension of the coefficients give y[(n' + L/2 - 1) mod 2K]
+// (reference sfb1d :252-261 re-indexed: 2k + j - (L/2 - 1) = n  <=>  n' = n - L/2 + 1 with n' = 2c + phase,
+// a[(c + i) mod K]); only the staging (wrapped rows / columns) and the store positions differ.
+template <int L, int U, bool PER>
 __device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, float2 (&wP)[L / 2][2],
                                         float2 (&wQ)[L / 2][2], bool emit, float*& y_ptr, int ypitch, int nv4,
-                                        bool row1_ok, bool vec4) {
+                                        bool row1_ok, bool vec4, const int (&ncol)[4], int nr0, int nr1) {
   using C = SfbCfg<L>;
   constexpr int HALF = C::HALF;
   float a[4][2 * C::NVB];  // [band][window]
@@ -70,49 +73,72 @@ __device__ __forceinline__ void sfb_row(const SfbParams& p, const float* srow, f
         }
         o[ph][e] = make_float2(__fadd_rn(s0.x, s1.x), __fadd_rn(s0.y, s1.y));
       }
+    if constexpr (PER) {
+      // y_ptr = plane base; nr0 / nr1 = rotated output rows of the pair (-1: outside the requested output),
+      // ncol[] = rotated output columns of the lane's four values
 #pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-      if (ph == 1 && !row1_ok) break;
-      float* q = y_ptr + ph * ypitch;
-      if (vec4 && nv4 == 4) {
-        *reinterpret_cast<float4*>(q) = make_float4(o[ph][0].x, o[ph][0].y, o[ph][1].x, o[ph][1].y);
-      } else {
-        if (0 < nv4) q[0] = o[ph][0].x;
-        if (1 < nv4) q[1] = o[ph][0].y;
-        if (2 < nv4) q[2] = o[ph][1].x;
-        if (3 < nv4) q[3] = o[ph][1].y;
+      for (int ph = 0; ph < 2; ++ph) {
+        const int nr = ph ? nr1 : nr0;
+        if (nr < 0) continue;
+        float* q = y_ptr + (long long)nr * ypitch;
+        if (ncol[0] >= 0) q[ncol[0]] = o[ph][0].x;
+        if (ncol[1] >= 0) q[ncol[1]] = o[ph][0].y;
+        if (ncol[2] >= 0) q[ncol[2]] = o[ph][1].x;
+        if (ncol[3] >= 0) q[ncol[3]] = o[ph][1].y;
       }
+    } else {
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        if (ph == 1 && !row1_ok) break;
+        float* q = y_ptr + ph * ypitch;
+        if (vec4 && nv4 == 4) {
+          *reinterpret_cast<float4*>(q) = make_float4(o[ph][0].x, o[ph][0].y, o[ph][1].x, o[ph][1].y);
+        } else {
+          if (0 < nv4) q[0] = o[ph][0].x;
+          if (1 < nv4) q[1] = o[ph][0].y;
+          if (2 < nv4) q[2] = o[ph][1].x;
+          if (3 < nv4) q[3] = o[ph][1].y;
+        }
+      }
+      y_ptr += 2 * ypitch;
     }
-    y_ptr += 2 * ypitch;
   }
 }
 
-template <int L, int V>
+template <int L, int V, bool PER>
 __device__ __forceinline__ void sfb_stage_dispatch(int vv, const SfbParams& p, const float* stage,
                                                    float2 (&wP)[L / 2][2], float2 (&wQ)[L / 2][2], int rho0,
-                                                   int rho_end, int m0, float*& y_ptr, int ypitch, int nv4, bool vec4) {
+                                                   int rho_end, int m0, float*& y_ptr, int ypitch, int nv4, bool vec4,
+                                                   const int (&ncol)[4]) {
   using C = SfbCfg<L>;
   if constexpr (V < C::UNS) {
     if (vv == V) {
-      {
-        const int rho = rho0;                             // coefficient row index relative to the chunk start
+#pragma unroll
+      for (int r = 0; r < C::KR; ++r) {
+        const int rho = rho0 + r;                         // coefficient row index relative to the chunk start
         const bool emit = (rho >= C::HALF - 1) && (rho < rho_end);
-        const int n0 = 2 * (m0 + rho - (C::HALF - 1));    // first output row of the pair
-        sfb_row<L, C::KR * V>(p, stage, wP, wQ, emit, y_ptr, ypitch, nv4, n0 + 1 < p.Ho, vec4);
-      }
-      if constexpr (C::KR == 2) {
-        const int rho = rho0 + 1;
-        const bool emit = (rho >= C::HALF - 1) && (rho < rho_end);
-        const int n0 = 2 * (m0 + rho - (C::HALF - 1));
-        sfb_row<L, C::KR * V + 1>(p, stage + 4 * C::SWB, wP, wQ, emit, y_ptr, ypitch, nv4, n0 + 1 < p.Ho, vec4);
+        const int n0 = 2 * (m0 + rho - (C::HALF - 1));    // first output row of the pair (before rotation if PER)
+        int nr0 = -1, nr1 = -1;
+        if (PER && emit) {
+          const int N = 2 * p.Hc;
+          nr0 = n0 + C::HALF - 1; if (nr0 >= N) nr0 -= N;
+          nr1 = n0 + C::HALF;     if (nr1 >= N) nr1 -= N;
+          if (nr0 >= p.Ho) nr0 = -1;
+          if (nr1 >= p.Ho) nr1 = -1;
+        }
+        if (r == 0)
+          sfb_row<L, C::KR * V, PER>(p, stage, wP, wQ, emit, y_ptr, ypitch, nv4, n0 + 1 < p.Ho, vec4, ncol, nr0, nr1);
+        else
+          sfb_row<L, C::KR * V + (C::KR - 1), PER>(p, stage + 4 * C::SWB, wP, wQ, emit, y_ptr, ypitch, nv4, n0 + 1 < p.Ho,
+                                                   vec4, ncol, nr0, nr1);
       }
     } else {
-      sfb_stage_dispatch<L, V + 1>(vv, p, stage, wP, wQ, rho0, rho_end, m0, y_ptr, ypitch, nv4, vec4);
+      sfb_stage_dispatch<L, V + 1, PER>(vv, p, stage, wP, wQ, rho0, rho_end, m0, y_ptr, ypitch, nv4, vec4, ncol);
     }
   }
 }
 
-template <int L>
+template <int L, bool PER = false>
 __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbParams p, int n_strips, int n_chunks,
                                                    int CH /* output row pairs per chunk */) {
   using C = SfbCfg<L>;
@@ -125,7 +151,7 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
   const int plane = (int)(item / n_chunks);
 
   const int c0 = strip * 64;                       // first coefficient column (= pair index) of the strip
-  const int npairs_h = (p.Ho + 1) >> 1;
+  const int npairs_h = PER ? p.Hc : (p.Ho + 1) >> 1;
   const int m0 = chunk * CH;
   const int m1 = imin(m0 + CH, npairs_h);
   const int n_rows = (m1 - m0) + C::HALF - 1;      // coefficient rows m0 .. m1-1+HALF-1
@@ -138,16 +164,23 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
   const long long band = (long long)p.Hc * p.Wc;
   const float* bptr[4];
   int bpitch[4];
-  bptr[0] = p.ll + (long long)plane * p.llps + c0;
+  bptr[0] = p.ll + (long long)plane * p.llps;
   bpitch[0] = p.llpitch;
 #pragma unroll
   for (int b = 1; b < 4; ++b) {
-    bptr[b] = p.highs ? p.highs + ((long long)plane * 3 + (b - 1)) * band + c0 : nullptr;
+    bptr[b] = p.highs ? p.highs + ((long long)plane * 3 + (b - 1)) * band : nullptr;
     bpitch[b] = p.Wc;
   }
-  const bool ok0 = (c0 + lane) < p.Wc;
-  const bool ok1 = (c0 + 32 + lane) < p.Wc;
-  const bool ok2 = (lane < C::HALF - 1) && ((c0 + 64 + lane) < p.Wc);
+  // the three 32-lane column copies of a band row: coefficient columns c0 + lane + {0, 32, 64}; PER wraps them
+  int colw[3];
+  bool okc[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int cidx = c0 + lane + 32 * j;
+    const bool in_lanes = (j < 2) || (lane < C::HALF - 1);
+    okc[j] = in_lanes && (PER ? (cidx < p.Wc + C::HALF - 1) : (cidx < p.Wc));
+    colw[j] = PER ? cidx % p.Wc : cidx;
+  }
 
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + 4 * lane;
   int slot_i = 0;
@@ -158,16 +191,18 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
       const unsigned dst = ring_s + slot * (C::STAGE * 4);
 #pragma unroll
       for (int r = 0; r < C::KR; ++r) {
-        const int k = m0 + C::KR * t + r;
-        if (k < p.Hc && C::KR * t + r < n_rows) {
+        int k = m0 + C::KR * t + r;
+        bool row_ok = (C::KR * t + r < n_rows);
+        if (PER) k %= p.Hc; else row_ok = row_ok && (k < p.Hc);
+        if (row_ok) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             if (bptr[b] == nullptr) continue;
-            const float* src = bptr[b] + (long long)k * bpitch[b] + lane;
+            const float* src = bptr[b] + (long long)k * bpitch[b];
             const unsigned d = dst + (r * 4 + b) * (C::SWB * 4);
-            if (ok0) cp_async4_s(d, src);
-            if (ok1) cp_async4_s(d + 128, src + 32);
-            if (ok2) cp_async4_s(d + 256, src + 64);
+            if (okc[0]) cp_async4_s(d, src + colw[0]);
+            if (okc[1]) cp_async4_s(d + 128, src + colw[1]);
+            if (okc[2]) cp_async4_s(d + 256, src + colw[2]);
           }
         }
       }
@@ -184,8 +219,19 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
     for (int c = 0; c < 2; ++c) { wP[j][c] = make_float2(0.f, 0.f); wQ[j][c] = make_float2(0.f, 0.f); }
 
   const int col0 = 2 * c0 + 4 * lane;
-  float* y_ptr = p.y + (long long)plane * p.yps + (long long)(2 * m0) * p.ypitch + col0;
+  float* y_ptr = PER ? p.y + (long long)plane * p.yps
+                     : p.y + (long long)plane * p.yps + (long long)(2 * m0) * p.ypitch + col0;
   const int nv4 = imax(0, imin(4, p.Wo - col0));
+  int ncol[4] = {-1, -1, -1, -1};
+  if (PER) {
+    const int N = 2 * p.Wc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int c = col0 + q + C::HALF - 1;
+      if (c >= N) c -= N;
+      ncol[q] = (col0 + q < N && c < p.Wo) ? c : -1;
+    }
+  }
   const bool vec4 = ((p.ypitch & 3) == 0) && ((p.yps & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
 
   int vv = 0, slot_a = 0;
@@ -196,29 +242,37 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
     issue(t + C::NS - 1);
     const float* stage = ring + slot_a * C::STAGE + 2 * lane;
     slot_a = (slot_a + 1 == C::NS) ? 0 : slot_a + 1;
-    sfb_stage_dispatch<L, 0>(vv, p, stage, wP, wQ, C::KR * t, n_rows, m0, y_ptr, p.ypitch, nv4, vec4);
+    sfb_stage_dispatch<L, 0, PER>(vv, p, stage, wP, wQ, C::KR * t, n_rows, m0, y_ptr, p.ypitch, nv4, vec4, ncol);
     vv = (vv + 1 == C::UNS) ? 0 : vv + 1;
   }
   cp_async_wait<0>();
 }
 
-template <int L>
-inline int launch_sfb_stream(const SfbParams& p, cudaStream_t stream) {
+template <int L, bool PER>
+inline int launch_sfb_stream_m(const SfbParams& p, cudaStream_t stream) {
   using C = SfbCfg<L>;
-  const int n_strips = (((p.Wo + 1) >> 1) + 63) / 64;
+  const int npairs_w = PER ? p.Wc : (p.Wo + 1) >> 1;
+  const int npairs_h = PER ? p.Hc : (p.Ho + 1) >> 1;
+  const int n_strips = (npairs_w + 63) / 64;
   int n_chunks, CH;
-  static const int conc = resident_warps(sfb2d_stream<L>, C::SMEM_BYTES);
-  pick_chunks((long long)p.planes * n_strips, (p.Ho + 1) >> 1, 16, L / 2 + 8, conc, &n_chunks, &CH);
+  static const int conc = resident_warps(sfb2d_stream<L, PER>, C::SMEM_BYTES);
+  pick_chunks((long long)p.planes * n_strips, npairs_h, 16, L / 2 + 8, conc, &n_chunks, &CH);
   const long long blocks = (long long)p.planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 2147483647LL) return kNoFastPath;
-  sfb2d_stream<L><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
+  sfb2d_stream<L, PER><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH);
   return 0;
+}
+
+template <int L>
+inline int launch_sfb_stream(const SfbParams& p, cudaStream_t stream) {
+  if (p.mode == B200W_MODE_PERIODIZATION) return launch_sfb_stream_m<L, true>(p, stream);
+  return launch_sfb_stream_m<L, false>(p, stream);
 }
 
 inline int try_launch_sfb(const SfbParams& p, cudaStream_t stream) {
   if (g_force_generic) return kNoFastPath;
-  if (p.Lw != p.Lh || p.mode == B200W_MODE_PERIODIZATION) return kNoFastPath;
+  if (p.Lw != p.Lh) return kNoFastPath;
   if (p.planes == 0) return 0;
   switch (p.Lw) {
     case 2: return launch_sfb_stream<2>(p, stream);
