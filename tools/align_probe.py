@@ -21,12 +21,12 @@ def t(fn, reps=10):
 import ctypes
 from pytorch_wavelets_b200 import _ffi
 _ffi.lib().b200w_debug_set_balanced.argtypes = [ctypes.c_int]
-for norows in [int(v) for v in os.environ.get('BALANCED', '0').split(',')]:
-  _ffi.lib().b200w_debug_set_balanced(norows)
+for balanced in [int(v) for v in os.environ.get('BALANCED', '0').split(',')]:
+  _ffi.lib().b200w_debug_set_balanced(balanced)
   for S in [int(v) for v in os.environ.get('SIZES', '506,508,510,512,259,133').split(',')]:
     x = big[..., :S, :S] if S > 300 else big.view(-1, 32, 512, 512)[:128, :, :S, :S]
     lo, hi = ll.afb2d_level(x, *taps, mode)
     ms = t(lambda: ll.afb2d_level(x, *taps, mode))
     Ho, Wo = hi.shape[-2:]
     gb = 4 * 4096 * (S * S + 4 * Ho * Wo) / 1e9
-    print(json.dumps({'balanced': norows, 'S': S, 'Wo': Wo, 'ms': round(ms, 4), 'GBps': round(gb / ms * 1e3, 1)}))
+    print(json.dumps({'balanced': balanced, 'S': S, 'Wo': Wo, 'ms': round(ms, 4), 'GBps': round(gb / ms * 1e3, 1)}))

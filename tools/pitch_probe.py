@@ -8,8 +8,7 @@ from pytorch_wavelets_b200 import _ffi
 from pytorch_wavelets_b200.dwt import lowlevel as ll
 
 lib = _ffi.lib()
-for fn in ('b200w_debug_set_norows', 'b200w_debug_set_hipitch'):
-    getattr(lib, fn).argtypes = [ctypes.c_int]
+lib.b200w_debug_set_hipitch.argtypes = [ctypes.c_int]
 f = pw.DWTForward(J=1, wave='db4', mode='symmetric').cuda()
 taps = [_ffi.host_taps(t) for t in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
 mode = ll.mode_to_int('symmetric')
@@ -31,7 +30,6 @@ def run(hip, llp):
     for _ in range(10): call()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 10
-lib.b200w_debug_set_norows(1)
 gb = 4 * P * (S * S + 4 * Ho * Wo) / 1e9
 for hip, llp in ((Wo, Wo), (Wo, 288), (288, 288), (264, 264), (260, 260)):
     lib.b200w_debug_set_hipitch(0 if hip == Wo else hip)
