@@ -182,6 +182,45 @@ int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr,
                   const float* h0, int L0, const float* h1, int L1,
                   int mode, float magbias, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Generic-kernel variants.  Every entry point above picks a specialised streaming kernel when one
+ * exists for the filter lengths / layout / alignment it is given and otherwise runs the generic tile
+ * kernel (any filter length <= B200W_MAX_TAPS, any mode, any layout).  The *_generic symbols take the
+ * same arguments and always run the generic tile kernel: an independent second implementation of the
+ * same arithmetic, used by the parity tests for A/B checks (selection is per call -- the library keeps
+ * no mode switch or any other global mutable state).
+ */
+int b200w_dwt_afb2d_generic(const float* x, long long x_plane_stride, int x_pitch,
+                            float* ll, long long ll_plane_stride, int ll_pitch, float* highs,
+                            int planes, int H, int W,
+                            const float* fw_lo, const float* fw_hi, int Lw,
+                            const float* fh_lo, const float* fh_hi, int Lh, int mode, void* stream);
+int b200w_dwt_sfb2d_generic(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
+                            float* y, long long y_plane_stride, int y_pitch,
+                            int planes, int Hc, int Wc, int Ho, int Wo,
+                            const float* gh_lo, const float* gh_hi, int Lh,
+                            const float* gw_lo, const float* gw_hi, int Lw, int mode, void* stream);
+int b200w_dtcwt_fwd_j1_generic(const float* x, long long x_plane_stride, int x_pitch,
+                               float* ll, long long ll_plane_stride, int ll_pitch,
+                               float* highs, const long long hs[6], int N, int C, int H, int W,
+                               const float* h0, int L0, const float* h1, int L1, int mode, void* stream);
+int b200w_dtcwt_fwd_j2plus_generic(const float* x, long long x_plane_stride, int x_pitch,
+                                   float* ll, long long ll_plane_stride, int ll_pitch,
+                                   float* highs, const long long hs[6], int N, int C, int H, int W,
+                                   const float* h0a, const float* h1a, const float* h0b, const float* h1b,
+                                   int m, void* stream);
+int b200w_dtcwt_inv_j1_generic(const float* ll, long long ll_plane_stride, int ll_pitch,
+                               const float* highs, const long long hs[6],
+                               float* y, long long y_plane_stride, int y_pitch, int N, int C, int H, int W,
+                               const float* g0, int L0, const float* g1, int L1, int mode, void* stream);
+int b200w_dtcwt_inv_j2plus_generic(const float* ll, long long ll_plane_stride, int ll_pitch,
+                                   const float* highs, const long long hs[6],
+                                   float* y, long long y_plane_stride, int y_pitch, int N, int C, int H, int W,
+                                   const float* g0a, const float* g1a, const float* g0b, const float* g1b,
+                                   int m, void* stream);
+int b200w_scat_j1_generic(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
+                          const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

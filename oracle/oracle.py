@@ -213,6 +213,7 @@ def dtcwt_inv_j1(ll, highs, g0, g1, o_dim=2, ri_dim=-1, mode='symmetric'):
         _, hs = highs_shape_strides(N, C, H // 2, W // 2, o_dim, ri_dim)
     else:
         hs = [0] * 6
+        mode = 'symmetric'   # reference quirk: the low-pass-only path ignores `mode` (transform_funcs.py:158-159)
     g0, g1 = _taps(g0, dtype), _taps(g1, dtype)
     y = np.empty((N, C, H, W), dtype)
     fn = getattr(lib(), 'orc_dtcwt_inv_j1' + sfx)

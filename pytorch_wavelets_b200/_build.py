@@ -10,16 +10,24 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libb200wave.so')
-SOURCES = ['b200wave.cu']
-HEADERS = ['common.h', 'tile_kernels.h', 'launch_params.h', 'fast_kernels.cuh', 'fast_dtcwt.cuh', 'fast_inverse.cuh', os.path.join('..', '..', 'include', 'b200wave.h')]
+OBJ = os.path.join(HERE, 'build')   # object files (git-ignored)
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-lineinfo', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-shared',
+    '-Xcompiler', '-fPIC',
     '--expt-relaxed-constexpr',
-    '-cudart', 'static',
 ]
+LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static']
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))] + \
+        [os.path.join(HERE, '..', 'include', 'b200wave.h'), os.path.abspath(__file__)]
 
 
 def nvcc():
@@ -29,31 +37,56 @@ def nvcc():
     return exe
 
 
+def _newest_header():
+    return max(os.path.getmtime(h) for h in headers() if os.path.exists(h))
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return _newest_header() > t or any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in sources())
 
 
-def build(force=False, verbose=False, out=None, extra_flags=()):
-    """Compile the library.  ``out`` / ``extra_flags`` build an experimental variant next to the default one
-    (see profiles/r01_notes.md, "A/B discipline"); the package itself only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
-    target = out or SO
-    if out is None and not force and not needs_build():
-        return SO
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', target] + [os.path.join(CSRC, s) for s in SOURCES]
+def _run(cmd):
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc wants the system g++
     env.pop('CC', None)
     env.pop('CXX', None)
     r = subprocess.run(cmd + ['-ccbin', '/usr/bin/g++'], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + r.stdout)
+        raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """Compile every translation unit of csrc/ (in parallel, one nvcc per .cu, objects cached under build/) and link
+    libb200wave.so.  ``out`` / ``extra_flags`` build an experimental variant next to the default one (objects are
+    then not cached); the package only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
+    from concurrent.futures import ThreadPoolExecutor
+    target = out or SO
+    if out is None and not force and not needs_build():
+        return SO
+    variant = out is not None or bool(extra_flags)
+    objdir = os.path.join(OBJ, 'variant_%d' % os.getpid()) if variant else OBJ
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = _newest_header()
+    jobs = []
+    objs = []
+    for src in sources():
+        o = os.path.join(objdir, src[:-3] + '.o')
+        objs.append(o)
+        sp = os.path.join(CSRC, src)
+        if force or variant or not os.path.exists(o) or os.path.getmtime(o) < max(hdr_t, os.path.getmtime(sp)):
+            jobs.append([nvcc()] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) +
+                        ['-c', '-o', o, sp])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        logs = list(ex.map(_run, jobs))
+    log = _run([nvcc()] + LINK_FLAGS + ['-o', target] + objs)
     if verbose:
-        print(r.stdout)
+        print('\n'.join(logs) + log)
+    if variant:
+        shutil.rmtree(objdir, ignore_errors=True)
     return target
 
 

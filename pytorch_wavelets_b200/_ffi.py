@@ -25,6 +25,8 @@ SYMBOLS = [
     'b200w_dwt_afb2d', 'b200w_dwt_sfb2d', 'b200w_dtcwt_fwd_j1', 'b200w_dtcwt_fwd_j2plus', 'b200w_dtcwt_inv_j1',
     'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1',
 ]
+KERNEL_ENTRIES = SYMBOLS[5:12]
+SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES]
 
 
 class B200WaveError(RuntimeError):
@@ -58,11 +60,33 @@ def lib():
                                              c_int, pf, pf, pf, pf, c_int, c_vp]
         L.b200w_scat_j1.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, pf, c_int, pf, c_int, c_int,
                                     ctypes.c_float, c_vp]
-        for s in ('b200w_debug_force_generic',):
-            getattr(L, s).argtypes = [c_int]
-            getattr(L, s).restype = None
+        for s in KERNEL_ENTRIES:
+            getattr(L, s + '_generic').argtypes = getattr(L, s).argtypes
         _lib = L
     return _lib
+
+
+# Which implementation the launch wrappers call: the auto-selecting entry points, or (inside
+# ``with generic_kernels():``, used by the A/B parity tests) the *_generic ones.  This switch lives in the Python
+# shell; the C library itself has no global state.
+_USE_GENERIC = False
+
+
+class generic_kernels(object):
+    def __enter__(self):
+        global _USE_GENERIC
+        self.prev, _USE_GENERIC = _USE_GENERIC, True
+        return self
+
+    def __exit__(self, *exc):
+        global _USE_GENERIC
+        _USE_GENERIC = self.prev
+        return False
+
+
+def entry(name):
+    """The C-ABI function for a kernel entry point (honours ``generic_kernels``)."""
+    return getattr(lib(), name + '_generic' if _USE_GENERIC else name)
 
 
 def check(rc, what):
@@ -102,15 +126,31 @@ def host_taps(t):
         return t
     if not isinstance(t, torch.Tensor):
         return HostTaps(np.asarray(t, dtype=np.float64))
+    # key: the version counter (in-place ops, optimiser steps, load_state_dict) AND the storage address
+    # (`p.data = new_tensor` rebinding).  In-place edits made THROUGH `.data` (`p.data.mul_(2)`) bump neither:
+    # call invalidate_host_taps(module_or_tensor) after such an edit.
+    key = (t._version, t.data_ptr())
     cached = getattr(t, '_b200w_host_taps', None)
-    if cached is not None and cached[0] == t._version:
+    if cached is not None and cached[0] == key:
         return cached[1]
     h = HostTaps(t.detach().to('cpu', torch.float64).numpy())
     try:
-        t._b200w_host_taps = (t._version, h)
+        t._b200w_host_taps = (key, h)
     except Exception:
         pass
     return h
+
+
+def invalidate_host_taps(obj):
+    """Drop the cached host copies of filter taps of a tensor, or of every parameter / buffer of a module
+    (needed only after editing filters in place through ``.data``, which no version counter sees)."""
+    ts = [obj] if isinstance(obj, torch.Tensor) else list(obj.parameters()) + list(obj.buffers())
+    for t in ts:
+        if hasattr(t, '_b200w_host_taps'):
+            try:
+                del t._b200w_host_taps
+            except Exception:
+                t._b200w_host_taps = None
 
 
 # ---- tensors ------------------------------------------------------------------------------------------

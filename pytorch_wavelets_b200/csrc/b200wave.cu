@@ -1,13 +1,14 @@
 // b200wave.cu -- libb200wave.so: C ABI (include/b200wave.h) + CUDA launchers, sm_100a only.
 //
-// Build (see pytorch_wavelets_b200/_build.py):
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC \
-//        -o libb200wave.so b200wave.cu
+// Build (see pytorch_wavelets_b200/_build.py): every .cu of this directory is compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -c
+// in parallel and linked into libb200wave.so.  This unit holds the C ABI and the generic tile kernels; the
+// streaming kernels live in k_*.cu behind fast_api.h.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
 #include "launch_params.h"
-#include "fast_kernels.cuh"
+#include "fast_api.h"
 
 namespace b200w {
 constexpr int NT = 256;
@@ -64,6 +65,95 @@ int launch_tile(K kernel, const P& p, long long blocks, int smem_floats, void* s
 
 }  // namespace
 
+namespace {
+
+static int dwt_afb2d_impl(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
+                    int ll_pitch, float* highs, int planes, int H, int W, const float* fw_lo, const float* fw_hi,
+                    int Lw, const float* fh_lo, const float* fh_hi, int Lh, int mode, void* stream, bool generic) {
+  AfbParams p;
+  int rc = build_afb(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, planes, H, W, fw_lo,
+                     fw_hi, Lw, fh_lo, fh_hi, Lh, mode);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_afb(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_afb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, afb_smem_floats(Lw, Lh), stream);
+}
+
+static int dwt_sfb2d_impl(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs, float* y,
+                    long long y_plane_stride, int y_pitch, int planes, int Hc, int Wc, int Ho, int Wo,
+                    const float* gh_lo, const float* gh_hi, int Lh, const float* gw_lo, const float* gw_hi, int Lw,
+                    int mode, void* stream, bool generic) {
+  SfbParams p;
+  int rc = build_sfb(p, ll, ll_plane_stride, ll_pitch, highs, y, y_plane_stride, y_pitch, planes, Hc, Wc, Ho, Wo,
+                     gh_lo, gh_hi, Lh, gw_lo, gw_hi, Lw, mode);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_sfb(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_sfb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, sfb_smem_floats(Lh, Lw), stream);
+}
+
+static int dtcwt_fwd_j1_impl(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
+                       int ll_pitch, float* highs, const long long hs[6], int N, int C, int H, int W,
+                       const float* h0, int L0, const float* h1, int L1, int mode, void* stream, bool generic) {
+  DtParams p;
+  int rc = build_fwd_j1(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0, L0,
+                        h1, L1, mode);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_fwd_j1(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_fwd_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj1_smem_floats(L0, L1), stream);
+}
+
+static int dtcwt_fwd_j2plus_impl(const float* x, long long x_plane_stride, int x_pitch, float* ll,
+                           long long ll_plane_stride, int ll_pitch, float* highs, const long long hs[6], int N,
+                           int C, int H, int W, const float* h0a, const float* h1a, const float* h0b,
+                           const float* h1b, int m, void* stream, bool generic) {
+  DtParams p;
+  int rc = build_fwd_j2plus(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W,
+                            h0a, h1a, h0b, h1b, m);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_fwd_j2plus(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_fwd_j2plus_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj2_smem_floats(m), stream);
+}
+
+static int dtcwt_inv_j1_impl(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
+                       const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C, int H,
+                       int W, const float* g0, int L0, const float* g1, int L1, int mode, void* stream, bool generic) {
+  DtParams p;
+  int rc = build_inv_j1(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0, L0,
+                        g1, L1, mode);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_inv_j1(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_inv_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj1_smem_floats(L0, L1), stream);
+}
+
+static int dtcwt_inv_j2plus_impl(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
+                           const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C,
+                           int H, int W, const float* g0a, const float* g1a, const float* g0b, const float* g1b,
+                           int m, void* stream, bool generic) {
+  DtParams p;
+  int rc = build_inv_j2plus(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W,
+                            g0a, g1a, g0b, g1b, m);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_inv_j2plus(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_inv_j2plus_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj2_smem_floats(m), stream);
+}
+
+static int scat_j1_impl(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
+                  const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream, bool generic) {
+  DtParams p;
+  int rc = build_scat_j1(p, x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias);
+  if (rc) return rc;
+  rc = generic ? fast::kNoFastPath : fast::try_launch_scat_j1(p, (cudaStream_t)stream);
+  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+  return launch_tile(k_scat_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj1_smem_floats(L0, L1), stream);
+}
+
+}  // namespace
+
 extern "C" {
 
 int b200w_version(void) { return B200W_VERSION; }
@@ -89,96 +179,82 @@ int b200w_dwt_rec_len(int k, int flen, int mode) { return rec_len(k, flen, mode)
 int b200w_dwt_afb2d(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
                     int ll_pitch, float* highs, int planes, int H, int W, const float* fw_lo, const float* fw_hi,
                     int Lw, const float* fh_lo, const float* fh_hi, int Lh, int mode, void* stream) {
-  AfbParams p;
-  int rc = build_afb(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, planes, H, W, fw_lo,
-                     fw_hi, Lw, fh_lo, fh_hi, Lh, mode);
-  if (rc) return rc;
-  p.hipitch = fast::g_tune_hipitch;
-  rc = fast::try_launch_afb(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_afb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, afb_smem_floats(Lw, Lh), stream);
+  return dwt_afb2d_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, planes, H, W, fw_lo, fw_hi, Lw, fh_lo, fh_hi, Lh, mode, stream, false);
+}
+int b200w_dwt_afb2d_generic(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
+                    int ll_pitch, float* highs, int planes, int H, int W, const float* fw_lo, const float* fw_hi,
+                    int Lw, const float* fh_lo, const float* fh_hi, int Lh, int mode, void* stream) {
+  return dwt_afb2d_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, planes, H, W, fw_lo, fw_hi, Lw, fh_lo, fh_hi, Lh, mode, stream, true);
 }
 
 int b200w_dwt_sfb2d(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs, float* y,
                     long long y_plane_stride, int y_pitch, int planes, int Hc, int Wc, int Ho, int Wo,
                     const float* gh_lo, const float* gh_hi, int Lh, const float* gw_lo, const float* gw_hi, int Lw,
                     int mode, void* stream) {
-  SfbParams p;
-  int rc = build_sfb(p, ll, ll_plane_stride, ll_pitch, highs, y, y_plane_stride, y_pitch, planes, Hc, Wc, Ho, Wo,
-                     gh_lo, gh_hi, Lh, gw_lo, gw_hi, Lw, mode);
-  if (rc) return rc;
-  rc = fast::try_launch_sfb(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_sfb2d_tile, p, (long long)planes * p.tiles_x * p.tiles_y, sfb_smem_floats(Lh, Lw), stream);
+  return dwt_sfb2d_impl(ll, ll_plane_stride, ll_pitch, highs, y, y_plane_stride, y_pitch, planes, Hc, Wc, Ho, Wo, gh_lo, gh_hi, Lh, gw_lo, gw_hi, Lw, mode, stream, false);
+}
+int b200w_dwt_sfb2d_generic(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs, float* y,
+                    long long y_plane_stride, int y_pitch, int planes, int Hc, int Wc, int Ho, int Wo,
+                    const float* gh_lo, const float* gh_hi, int Lh, const float* gw_lo, const float* gw_hi, int Lw,
+                    int mode, void* stream) {
+  return dwt_sfb2d_impl(ll, ll_plane_stride, ll_pitch, highs, y, y_plane_stride, y_pitch, planes, Hc, Wc, Ho, Wo, gh_lo, gh_hi, Lh, gw_lo, gw_hi, Lw, mode, stream, true);
 }
 
 int b200w_dtcwt_fwd_j1(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
                        int ll_pitch, float* highs, const long long hs[6], int N, int C, int H, int W,
                        const float* h0, int L0, const float* h1, int L1, int mode, void* stream) {
-  DtParams p;
-  int rc = build_fwd_j1(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0, L0,
-                        h1, L1, mode);
-  if (rc) return rc;
-  rc = fast::try_launch_fwd_j1(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_fwd_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj1_smem_floats(L0, L1), stream);
+  return dtcwt_fwd_j1_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0, L0, h1, L1, mode, stream, false);
+}
+int b200w_dtcwt_fwd_j1_generic(const float* x, long long x_plane_stride, int x_pitch, float* ll, long long ll_plane_stride,
+                       int ll_pitch, float* highs, const long long hs[6], int N, int C, int H, int W,
+                       const float* h0, int L0, const float* h1, int L1, int mode, void* stream) {
+  return dtcwt_fwd_j1_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0, L0, h1, L1, mode, stream, true);
 }
 
 int b200w_dtcwt_fwd_j2plus(const float* x, long long x_plane_stride, int x_pitch, float* ll,
                            long long ll_plane_stride, int ll_pitch, float* highs, const long long hs[6], int N,
                            int C, int H, int W, const float* h0a, const float* h1a, const float* h0b,
                            const float* h1b, int m, void* stream) {
-  DtParams p;
-  int rc = build_fwd_j2plus(p, x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W,
-                            h0a, h1a, h0b, h1b, m);
-  if (rc) return rc;
-  rc = fast::try_launch_fwd_j2plus(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_fwd_j2plus_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj2_smem_floats(m), stream);
+  return dtcwt_fwd_j2plus_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0a, h1a, h0b, h1b, m, stream, false);
+}
+int b200w_dtcwt_fwd_j2plus_generic(const float* x, long long x_plane_stride, int x_pitch, float* ll,
+                           long long ll_plane_stride, int ll_pitch, float* highs, const long long hs[6], int N,
+                           int C, int H, int W, const float* h0a, const float* h1a, const float* h0b,
+                           const float* h1b, int m, void* stream) {
+  return dtcwt_fwd_j2plus_impl(x, x_plane_stride, x_pitch, ll, ll_plane_stride, ll_pitch, highs, hs, N, C, H, W, h0a, h1a, h0b, h1b, m, stream, true);
 }
 
 int b200w_dtcwt_inv_j1(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
                        const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C, int H,
                        int W, const float* g0, int L0, const float* g1, int L1, int mode, void* stream) {
-  DtParams p;
-  int rc = build_inv_j1(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0, L0,
-                        g1, L1, mode);
-  if (rc) return rc;
-  rc = fast::try_launch_inv_j1(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_inv_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj1_smem_floats(L0, L1), stream);
+  return dtcwt_inv_j1_impl(ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0, L0, g1, L1, mode, stream, false);
+}
+int b200w_dtcwt_inv_j1_generic(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
+                       const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C, int H,
+                       int W, const float* g0, int L0, const float* g1, int L1, int mode, void* stream) {
+  return dtcwt_inv_j1_impl(ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0, L0, g1, L1, mode, stream, true);
 }
 
 int b200w_dtcwt_inv_j2plus(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
                            const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C,
                            int H, int W, const float* g0a, const float* g1a, const float* g0b, const float* g1b,
                            int m, void* stream) {
-  DtParams p;
-  int rc = build_inv_j2plus(p, ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W,
-                            g0a, g1a, g0b, g1b, m);
-  if (rc) return rc;
-  rc = fast::try_launch_inv_j2plus(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_inv_j2plus_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, invj2_smem_floats(m), stream);
+  return dtcwt_inv_j2plus_impl(ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0a, g1a, g0b, g1b, m, stream, false);
+}
+int b200w_dtcwt_inv_j2plus_generic(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
+                           const long long hs[6], float* y, long long y_plane_stride, int y_pitch, int N, int C,
+                           int H, int W, const float* g0a, const float* g1a, const float* g0b, const float* g1b,
+                           int m, void* stream) {
+  return dtcwt_inv_j2plus_impl(ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0a, g1a, g0b, g1b, m, stream, true);
 }
 
 int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
                   const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream) {
-  DtParams p;
-  int rc = build_scat_j1(p, x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias);
-  if (rc) return rc;
-  rc = fast::try_launch_scat_j1(p, (cudaStream_t)stream);
-  if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-  return launch_tile(k_scat_j1_tile, p, (long long)N * C * p.tiles_x * p.tiles_y, fwdj1_smem_floats(L0, L1), stream);
+  return scat_j1_impl(x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias, stream, false);
 }
-
-/* Selects which implementation the forward entry points use: 0 = automatic (fast streaming kernels
- * where a specialisation exists, generic tile kernels otherwise), 1 = force the generic tile kernels.
- * Testing / benchmarking aid; process-wide. */
-void b200w_debug_force_generic(int on) { fast::g_force_generic = on; }
-/* knobs of the measurement probes (tools/align_probe.py, tools/pitch_probe.py, tools/quick_fwd.py) */
-void b200w_debug_set_want(int v) { fast::g_tune_want = v; }
-void b200w_debug_set_hipitch(int v) { fast::g_tune_hipitch = v; }
-void b200w_debug_set_balanced(int v) { fast::g_tune_balanced = v; }
+int b200w_scat_j1_generic(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
+                  const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream) {
+  return scat_j1_impl(x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias, stream, true);
+}
 
 }  // extern "C"

@@ -81,6 +81,11 @@ B200W_HD int ext_index(int i, int N, int mode) {
   }
 }
 
+// DTCWT level-1 extension: symmetric, or zero padding (reference dtcwt/lowlevel.py:75-79)
+B200W_HD int sym_or_zero(int i, int N, int sym) {
+  return sym ? ext_index(i, N, B200W_MODE_SYMMETRIC) : (((unsigned)i < (unsigned)N) ? i : -1);
+}
+
 B200W_HD int floordiv2(int a) { return a >> 1; }  // arithmetic shift == floor division by 2
 B200W_HD int imax(int a, int b) { return a > b ? a : b; }
 B200W_HD int imin(int a, int b) { return a < b ? a : b; }

@@ -1,3 +1,9 @@
+#pragma once
+#include "stream_common.cuh"
+
+namespace b200w {
+namespace fast {
+
 // fast_dtcwt.cuh -- streaming DTCWT forward kernels (included inside namespace b200w::fast by
 // fast_kernels.cuh).  Same machinery as the DWT kernel: per-warp strip, cp.async ring (StripLoader),
 // 128/64-bit conflict-free LDS for the pass along W, rotating register window for the pass along H,
@@ -214,7 +220,8 @@ inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = (p.W + 63) / 64;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  static const int conc = resident_warps(fwd_j1_stream<L0, L1, SCAT>, C::SMEM_BYTES);
+  static ConcCache conc_cache;
+  const int conc = resident_warps_dev(conc_cache, fwd_j1_stream<L0, L1, SCAT>, C::SMEM_BYTES);
   pick_chunks(planes * n_strips, p.H >> 1, 8, 8, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
@@ -225,7 +232,6 @@ inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
 
 template <bool SCAT>
 inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
-  if (g_force_generic) return kNoFastPath;
   if (!SCAT && !p.highs) return kNoFastPath;  // skip_hps: low-pass only, generic kernel
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 5 && p.L1 == 7) return launch_j1_stream<5, 7, SCAT>(p, stream);   // near_sym_a analysis
@@ -240,8 +246,8 @@ inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
   }
   return kNoFastPath;
 }
-inline int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<false>(p, stream); }
-inline int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<true>(p, stream); }
+int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<false>(p, stream); }
+int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<true>(p, stream); }
 
 // ================================================================================================
 // K4 fast: DTCWT level >= 2 forward, q-shift filters of even length MQ.
@@ -400,7 +406,8 @@ inline int launch_j2_stream(const DtParams& p, cudaStream_t stream) {
   const int n_strips = ((p.W >> 2) + 31) / 32;
   const long long planes = (long long)p.N * p.C;
   int n_chunks, CH;
-  static const int conc = resident_warps(fwd_j2plus_stream<MQ>, C::SMEM_BYTES);
+  static ConcCache conc_cache;
+  const int conc = resident_warps_dev(conc_cache, fwd_j2plus_stream<MQ>, C::SMEM_BYTES);
   pick_chunks(planes * n_strips, p.H >> 2, 4, 7, conc, &n_chunks, &CH);
   const long long blocks = planes * n_strips * n_chunks;
   if (blocks <= 0) return 0;
@@ -409,8 +416,7 @@ inline int launch_j2_stream(const DtParams& p, cudaStream_t stream) {
   return 0;
 }
 
-inline int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream) {
-  if (g_force_generic) return kNoFastPath;
+int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream) {
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 10) return launch_j2_stream<10>(p, stream);  // qshift_a, qshift_06
   if (p.L0 == 14) return launch_j2_stream<14>(p, stream);  // qshift_b
@@ -418,3 +424,7 @@ inline int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream) {
   if (p.L0 == 18) return launch_j2_stream<18>(p, stream);  // qshift_d
   return kNoFastPath;
 }
+
+
+}  // namespace fast
+}  // namespace b200w

@@ -1,0 +1,24 @@
+// fast_api.h -- host entry points of the specialised streaming kernels; each is defined in its own translation
+// unit (k_afb.cu, k_sfb.cu, k_dtcwt_fwd.cu, k_dtcwt_inv.cu, k_pyramid.cu) so the library builds in parallel.
+// Every function returns 0 when it launched, kNoFastPath when there is no specialisation for these parameters
+// (the caller then runs the generic tile kernel), or a negative B200W_E* code.  No global state.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace b200w {
+namespace fast {
+
+constexpr int kNoFastPath = 1;
+
+int try_launch_afb(const AfbParams& p, cudaStream_t stream);
+int try_launch_sfb(const SfbParams& p, cudaStream_t stream);
+int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream);
+int try_launch_scat_j1(const DtParams& p, cudaStream_t stream);
+int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream);
+int try_launch_inv_j1(const DtParams& p, cudaStream_t stream);
+int try_launch_inv_j2plus(const DtParams& p, cudaStream_t stream);
+
+}  // namespace fast
+}  // namespace b200w

@@ -211,10 +211,6 @@ B200W_D void sfb2d_tile(const SfbParams& p, int bid, float* smem) {
 // ================================================================================================
 // DTCWT helpers
 // ================================================================================================
-B200W_HD int sym_or_zero(int i, int N, int sym) {
-  return sym ? ext_index(i, N, B200W_MODE_SYMMETRIC) : (((unsigned)i < (unsigned)N) ? i : -1);
-}
-
 // q2c + orientation store (reference dtcwt/lowlevel.py:243-260, transform_funcs.py:61-72).
 // a,b / c,d = the 2x2 quad of one real subband; o1/o2 = orientation slots of w1 = (a-d, b+c), w2 = (a+d, b-c).
 B200W_D void q2c_store(float a, float b, float c, float d, float* hq, const long long* hs, int o1, int o2) {

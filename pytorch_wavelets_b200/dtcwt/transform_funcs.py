@@ -105,7 +105,7 @@ def fwd_j1(x, h0, h1, skip_hps, o5, ri, mode):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j1 %dx%d' % (H, W),
                                                     4 * N * C * H * W * (2 if skip_hps else 5)):
-            rc = L.b200w_dtcwt_fwd_j1(x.data_ptr(), xps, xpitch, ll.data_ptr(), H * W, W,
+            rc = _ffi.entry('b200w_dtcwt_fwd_j1')(x.data_ptr(), xps, xpitch, ll.data_ptr(), H * W, W,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                       N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n, mode, _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dtcwt_fwd_j1')
@@ -130,7 +130,7 @@ def fwd_j2plus(x, h0a, h1a, h0b, h1b, skip_hps, o5, ri):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j2plus %dx%d' % (H, W),
                                                     N * C * H * W * (5 if skip_hps else 8)):
-            rc = L.b200w_dtcwt_fwd_j2plus(x.data_ptr(), xps, xpitch, ll.data_ptr(), (H // 2) * (W // 2), W // 2,
+            rc = _ffi.entry('b200w_dtcwt_fwd_j2plus')(x.data_ptr(), xps, xpitch, ll.data_ptr(), (H // 2) * (W // 2), W // 2,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                           N, C, H, W, f[0].ptr, f[1].ptr, f[2].ptr, f[3].ptr, f[0].n,
                                           _ffi.stream_of(x))
@@ -171,11 +171,16 @@ def inv_j1(ll, highs, g0, g1, o5, ri, mode):
             if ll.shape[2] != 2 * sz['h'] or ll.shape[3] != 2 * sz['w']:
                 raise ValueError('low-pass {} does not match band-pass {}'.format(tuple(ll.shape), tuple(highs.shape)))
             N, C, H, W = ll.shape
+            if sz['n'] != N or sz['c'] != C:   # the kernel strides the band-pass with ll's N, C
+                raise ValueError('low-pass {} does not match band-pass {}'.format(tuple(ll.shape), tuple(highs.shape)))
         else:
             N, C, H, W = sz['n'], sz['c'], 2 * sz['h'], 2 * sz['w']
         _, hs = highs_shape_strides(N, C, H // 2, W // 2, o5, ri)
     else:
         N, C, H, W = ll.shape
+        # reference quirk: the low-pass-only path calls rowfilter(colfilter(ll, g0), g0) without `mode`,
+        # i.e. always with the default symmetric extension (transform_funcs.py:158-159)
+        mode = 1
     if H % 2 or W % 2:
         raise ValueError('level-1 DTCWT low-pass must have even height and width')
     ref = ll if ll is not None else highs
@@ -186,7 +191,7 @@ def inv_j1(ll, highs, g0, g1, o5, ri, mode):
     if N * C > 0:
         with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j1 %dx%d' % (H, W),
                                                       4 * N * C * H * W * (1 + (ll is not None) + 3 * (highs is not None))):
-            rc = L.b200w_dtcwt_inv_j1(None if ll is None else ll.data_ptr(), llps, llpitch,
+            rc = _ffi.entry('b200w_dtcwt_inv_j1')(None if ll is None else ll.data_ptr(), llps, llpitch,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                       y.data_ptr(), H * W, W, N, C, H, W, g0.ptr, g0.n, g1.ptr, g1.n, mode,
                                       _ffi.stream_of(ref))
@@ -205,7 +210,7 @@ def inv_j2plus(ll, highs, g0a, g1a, g0b, g1b, o5, ri):
     else:
         N, C, H, W = sz['n'], sz['c'], 2 * sz['h'], 2 * sz['w']
     if highs is not None:
-        if ll is not None and (H != 2 * sz['h'] or W != 2 * sz['w']):
+        if ll is not None and (H != 2 * sz['h'] or W != 2 * sz['w'] or sz['n'] != N or sz['c'] != C):
             raise ValueError('low-pass {} does not match band-pass {}'.format(tuple(ll.shape), tuple(highs.shape)))
         _, hs = highs_shape_strides(N, C, H // 2, W // 2, o5, ri)
     if H % 2 != 0:
@@ -220,7 +225,7 @@ def inv_j2plus(ll, highs, g0a, g1a, g0b, g1b, o5, ri):
     if N * C > 0:
         with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j2plus %dx%d' % (H, W),
                                                       4 * N * C * H * W * (4 + (ll is not None) + 3 * (highs is not None))):
-            rc = L.b200w_dtcwt_inv_j2plus(None if ll is None else ll.data_ptr(), llps, llpitch,
+            rc = _ffi.entry('b200w_dtcwt_inv_j2plus')(None if ll is None else ll.data_ptr(), llps, llpitch,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                           y.data_ptr(), 4 * H * W, 2 * W, N, C, H, W,
                                           f[0].ptr, f[1].ptr, f[2].ptr, f[3].ptr, f[0].n, _ffi.stream_of(ref))

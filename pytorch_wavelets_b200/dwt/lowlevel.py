@@ -116,7 +116,7 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dwt_afb2d %dx%d L%d' % (H, W, fw_lo.n),
                                                     4 * N * C * (H * W + 4 * Ho * Wo)):
-            rc = L.b200w_dwt_afb2d(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wp, Wp, highs.data_ptr(),
+            rc = _ffi.entry('b200w_dwt_afb2d')(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wp, Wp, highs.data_ptr(),
                                    N * C, H, W, fw_lo.ptr, fw_hi.ptr, fw_lo.n, fh_lo.ptr, fh_hi.ptr, fh_lo.n,
                                    mode, _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dwt_afb2d')
@@ -147,7 +147,7 @@ def sfb2d_level(ll, highs, gh_lo, gh_hi, gw_lo, gw_hi, mode, out_hw=None):
     if N * C > 0:
         with torch.cuda.device(ll.device), _ffi.span('dwt_sfb2d %dx%d L%d' % (Hc, Wc, gh_lo.n),
                                                      4 * N * C * ((1 if highs is None else 4) * Hc * Wc + Ho * Wo)):
-            rc = L.b200w_dwt_sfb2d(ll.data_ptr(), llps, llpitch, None if highs is None else highs.data_ptr(),
+            rc = _ffi.entry('b200w_dwt_sfb2d')(ll.data_ptr(), llps, llpitch, None if highs is None else highs.data_ptr(),
                                    y.data_ptr(), Ho * Wo, Wo, N * C, Hc, Wc, Ho, Wo,
                                    gh_lo.ptr, gh_hi.ptr, gh_lo.n, gw_lo.ptr, gw_hi.ptr, gw_lo.n, mode,
                                    _ffi.stream_of(ll))

@@ -41,8 +41,12 @@ class HostPipeline(object):
         torch.cuda.synchronize(self.device)
 
     def run(self, host_x):
-        """host_x: pinned (N, C, H, W) float32.  Returns the list of pinned host output tensors (valid after
-        the current stream has waited on this call, which it does before returning control)."""
+        """host_x: pinned (N, C, H, W) float32.  Returns the list of pinned host output tensors.  The copies are
+        asynchronous: the current STREAM waits for them before this returns, the HOST does not -- call
+        ``self.done.synchronize()`` (or ``torch.cuda.synchronize()``) before reading the host tensors on the CPU.
+        The output buffers are reused by the next ``run``; it waits for the previous one's copies first."""
+        if getattr(self, 'done', None) is not None:
+            self.done.synchronize()
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_h2d, self.s_cmp, self.s_d2h):
             s.wait_stream(cur)
@@ -71,6 +75,8 @@ class HostPipeline(object):
                     o.record_stream(self.s_d2h)
                     h[n0:n1].copy_(o, non_blocking=True)
             keep.append(outs)
+        self.done = torch.cuda.Event()
+        self.done.record(self.s_d2h)
         cur.wait_stream(self.s_d2h)
         cur.wait_stream(self.s_cmp)
         return self.host_out

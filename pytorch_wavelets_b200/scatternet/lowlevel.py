@@ -26,7 +26,7 @@ def scat_j1(x, h0o, h1o, mode, bias, want_aux):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('scat_j1 %dx%d' % (H, W),
                                                     N * C * H * W * (4 + 7 + (12 if want_aux else 0))):
-            rc = L.b200w_scat_j1(x.data_ptr(), z.data_ptr(), None if dre is None else dre.data_ptr(),
+            rc = _ffi.entry('b200w_scat_j1')(x.data_ptr(), z.data_ptr(), None if dre is None else dre.data_ptr(),
                                  None if dim is None else dim.data_ptr(), N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n,
                                  mode, float(bias), _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_scat_j1')

@@ -23,10 +23,10 @@ with torch.no_grad():
         g = pw.DTCWTInverse(biort=biort, qshift=qshift).cuda()
         c = f(x)
         r = {}
-        for name, force in (('stream', 0), ('generic', 1)):
-            lib.b200w_debug_force_generic(force)
-            r[name + '_fwd_ms'] = round(timeit(lambda: f(x)), 3)
-            r[name + '_inv_ms'] = round(timeit(lambda: g(c)), 3)
-        lib.b200w_debug_force_generic(0)
+        r['stream_fwd_ms'] = round(timeit(lambda: f(x)), 3)
+        r['stream_inv_ms'] = round(timeit(lambda: g(c)), 3)
+        with _ffi.generic_kernels():
+            r['generic_fwd_ms'] = round(timeit(lambda: f(x)), 3)
+            r['generic_inv_ms'] = round(timeit(lambda: g(c)), 3)
         out[biort + '/' + qshift] = r
 print(json.dumps(out))
