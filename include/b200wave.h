@@ -88,6 +88,29 @@ int b200w_dwt_afb2d(const float* x, long long x_plane_stride, int x_pitch,
                     int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1xJ  all J analysis levels in one call.  Replaces the level loop of DWTForward.forward, reference
+ *     dwt/transform2d.py:68-74 (J x AFB2D.apply with the low-pass fed back).
+ *   x      (planes, H, W) pitched as in K1
+ *   yl     (planes, H_J, W_J) contiguous: the final low-pass
+ *   highs  HOST array of J device pointers; highs[j] is level j+1's (planes, 3, H_j, W_j) contiguous tensor
+ *          (finest first, the reference's yh list); H_j = b200w_dwt_coeff_len(H_{j-1}, Lh, mode) etc.
+ *   When the fused pyramid kernel applies (equal even filter lengths <= 16, mode zero / symmetric / reflect,
+ *   16-byte aligned rows with W % 4 == 0, every level at least as large as the filter, the plan fits shared
+ *   memory) this is ONE kernel launch and the inter-level low-passes never touch device memory.  Otherwise the
+ *   levels run one K1 launch each and their intermediate low-passes live in `workspace` (caller-owned device
+ *   memory, at least b200w_dwt_forward_workspace(...) bytes, which is 0 when the fused kernel applies; the
+ *   same x / strides must be passed to both calls since the answer depends on the alignment of x).
+ */
+long long b200w_dwt_forward_workspace(const float* x, long long x_plane_stride, int x_pitch,
+                                      int planes, int H, int W, int J, int Lw, int Lh, int mode);
+int b200w_dwt_forward(const float* x, long long x_plane_stride, int x_pitch,
+                      int planes, int H, int W, int J,
+                      float* yl, float* const* highs,
+                      const float* fw_lo, const float* fw_hi, int Lw,
+                      const float* fh_lo, const float* fh_hi, int Lh,
+                      int mode, void* workspace, long long workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  one 2-D DWT synthesis level.          Replaces SFB2D.forward, reference dwt/lowlevel.py:671-680
  *     (sfb1d along H for (ll,lh) and (hl,hh), then along W; :226-271).
  *   ll     (planes, Hc, Wc) pitched;  highs (planes, 3, Hc, Wc) contiguous, or NULL = zeros
@@ -195,6 +218,11 @@ int b200w_dwt_afb2d_generic(const float* x, long long x_plane_stride, int x_pitc
                             int planes, int H, int W,
                             const float* fw_lo, const float* fw_hi, int Lw,
                             const float* fh_lo, const float* fh_hi, int Lh, int mode, void* stream);
+int b200w_dwt_forward_generic(const float* x, long long x_plane_stride, int x_pitch,
+                              int planes, int H, int W, int J, float* yl, float* const* highs,
+                              const float* fw_lo, const float* fw_hi, int Lw,
+                              const float* fh_lo, const float* fh_hi, int Lh,
+                              int mode, void* workspace, long long workspace_bytes, void* stream);
 int b200w_dwt_sfb2d_generic(const float* ll, long long ll_plane_stride, int ll_pitch, const float* highs,
                             float* y, long long y_plane_stride, int y_pitch,
                             int planes, int Hc, int Wc, int Ho, int Wo,

@@ -23,10 +23,10 @@ c_int = ctypes.c_int
 SYMBOLS = [
     'b200w_version', 'b200w_strerror', 'b200w_last_cuda_error', 'b200w_dwt_coeff_len', 'b200w_dwt_rec_len',
     'b200w_dwt_afb2d', 'b200w_dwt_sfb2d', 'b200w_dtcwt_fwd_j1', 'b200w_dtcwt_fwd_j2plus', 'b200w_dtcwt_inv_j1',
-    'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1',
+    'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1', 'b200w_dwt_forward',
 ]
-KERNEL_ENTRIES = SYMBOLS[5:12]
-SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES]
+KERNEL_ENTRIES = SYMBOLS[5:13]
+SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + ['b200w_dwt_forward_workspace']
 
 
 class B200WaveError(RuntimeError):
@@ -60,6 +60,10 @@ def lib():
                                              c_int, pf, pf, pf, pf, c_int, c_vp]
         L.b200w_scat_j1.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, pf, c_int, pf, c_int, c_int,
                                     ctypes.c_float, c_vp]
+        L.b200w_dwt_forward.argtypes = [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_vp),
+                                        pf, pf, c_int, pf, pf, c_int, c_int, c_vp, c_ll, c_vp]
+        L.b200w_dwt_forward_workspace.argtypes = [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+        L.b200w_dwt_forward_workspace.restype = c_ll
         for s in KERNEL_ENTRIES:
             getattr(L, s + '_generic').argtypes = getattr(L, s).argtypes
         _lib = L

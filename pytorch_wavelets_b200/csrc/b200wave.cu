@@ -248,6 +248,94 @@ int b200w_dtcwt_inv_j2plus_generic(const float* ll, long long ll_plane_stride, i
   return dtcwt_inv_j2plus_impl(ll, ll_plane_stride, ll_pitch, highs, hs, y, y_plane_stride, y_pitch, N, C, H, W, g0a, g1a, g0b, g1b, m, stream, true);
 }
 
+/* ---- whole-transform entry point: all J analysis levels of DWTForward.forward (reference dwt/transform2d.py:68-74) */
+
+static long long align256(long long n) { return (n + 255) / 256 * 256; }
+
+// intermediate low-pass buffers of the level-by-level path: level j writes buffer j % 2 with a 128-byte row pitch
+static void dwt_ws_layout(int planes, int H, int W, int J, int Lw, int Lh, int mode, long long bytes[2]) {
+  bytes[0] = bytes[1] = 0;
+  int h = H, w = W;
+  for (int j = 0; j + 1 < J; ++j) {
+    h = coeff_len(h, Lh, mode); w = coeff_len(w, Lw, mode);
+    if (h < 1 || w < 1) break;
+    const long long need = align256(4LL * planes * h * ((w + 31) / 32 * 32));
+    if (need > bytes[j & 1]) bytes[j & 1] = need;
+  }
+}
+
+long long b200w_dwt_forward_workspace(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W,
+                                      int J, int Lw, int Lh, int mode) {
+  if (!dwt_mode_ok(mode)) return B200W_EMODE;
+  if (planes < 0 || H < 1 || W < 1 || J < 1) return B200W_ESIZE;
+  if (Lw < 2 || Lh < 2 || Lw > kMaxTaps || Lh > kMaxTaps) return B200W_EFILTER;
+  if (Lw == Lh) {
+    PyrParams pp;
+    if (fast::plan_dwt_pyramid(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, mode) == 0) return 0;
+  }
+  long long b[2];
+  dwt_ws_layout(planes, H, W, J, Lw, Lh, mode, b);
+  return b[0] + b[1];
+}
+
+static int dwt_forward_impl(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W, int J,
+                            float* yl, float* const* highs, const float* fw_lo, const float* fw_hi, int Lw,
+                            const float* fh_lo, const float* fh_hi, int Lh, int mode, void* workspace,
+                            long long workspace_bytes, void* stream, bool generic) {
+  if (!dwt_mode_ok(mode)) return B200W_EMODE;
+  if (!x || !yl || !highs) return B200W_EARG;
+  if (planes < 0 || H < 1 || W < 1 || J < 1) return B200W_ESIZE;
+  if (Lw < 2 || Lh < 2) return B200W_EFILTER;
+  for (int j = 0; j < J; ++j)
+    if (!highs[j]) return B200W_EARG;
+  if (!generic && Lw == Lh) {
+    PyrParams pp;
+    if (fast::plan_dwt_pyramid(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, mode) == 0) {
+      int rc;
+      if ((rc = set_taps(pp.fw_lo, fw_lo, Lw)) || (rc = set_taps(pp.fw_hi, fw_hi, Lw)) ||
+          (rc = set_taps(pp.fh_lo, fh_lo, Lh)) || (rc = set_taps(pp.fh_hi, fh_hi, Lh)))
+        return rc;
+      pp.yl = yl;
+      for (int j = 0; j < kPyrMaxLevels; ++j) pp.highs[j] = (j < J) ? highs[j] : nullptr;
+      rc = fast::launch_dwt_pyramid(pp, (cudaStream_t)stream);
+      if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+    }
+  }
+  long long wb[2];
+  dwt_ws_layout(planes, H, W, J, Lw, Lh, mode, wb);
+  if (wb[0] + wb[1] > 0 && (!workspace || workspace_bytes < wb[0] + wb[1])) return B200W_EARG;
+  float* buf[2] = {static_cast<float*>(workspace), reinterpret_cast<float*>(static_cast<char*>(workspace) + wb[0])};
+  const float* src = x;
+  long long sps = x_plane_stride;
+  int spitch = x_pitch, h = H, w = W;
+  for (int j = 0; j < J; ++j) {
+    const int ho = coeff_len(h, Lh, mode), wo = coeff_len(w, Lw, mode);
+    if (ho < 1 || wo < 1) return B200W_ESIZE;
+    const bool last = (j == J - 1);
+    const int wp = last ? wo : (wo + 31) / 32 * 32;
+    float* ll = last ? yl : buf[j & 1];
+    const int rc = dwt_afb2d_impl(src, sps, spitch, ll, (long long)ho * wp, wp, highs[j], planes, h, w, fw_lo, fw_hi,
+                                  Lw, fh_lo, fh_hi, Lh, mode, stream, generic);
+    if (rc) return rc;
+    src = ll; sps = (long long)ho * wp; spitch = wp; h = ho; w = wo;
+  }
+  return B200W_OK;
+}
+
+int b200w_dwt_forward(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W, int J, float* yl,
+                      float* const* highs, const float* fw_lo, const float* fw_hi, int Lw, const float* fh_lo,
+                      const float* fh_hi, int Lh, int mode, void* workspace, long long workspace_bytes, void* stream) {
+  return dwt_forward_impl(x, x_plane_stride, x_pitch, planes, H, W, J, yl, highs, fw_lo, fw_hi, Lw, fh_lo, fh_hi, Lh,
+                          mode, workspace, workspace_bytes, stream, false);
+}
+int b200w_dwt_forward_generic(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W, int J,
+                              float* yl, float* const* highs, const float* fw_lo, const float* fw_hi, int Lw,
+                              const float* fh_lo, const float* fh_hi, int Lh, int mode, void* workspace,
+                              long long workspace_bytes, void* stream) {
+  return dwt_forward_impl(x, x_plane_stride, x_pitch, planes, H, W, J, yl, highs, fw_lo, fw_hi, Lw, fh_lo, fh_hi, Lh,
+                          mode, workspace, workspace_bytes, stream, true);
+}
+
 int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
                   const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream) {
   return scat_j1_impl(x, z, dre_dr, dim_dr, N, C, H, W, h0, L0, h1, L1, mode, magbias, stream, false);

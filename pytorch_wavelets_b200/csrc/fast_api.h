@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "common.h"
+#include "pyramid_plan.h"
 
 namespace b200w {
 namespace fast {
@@ -19,6 +20,12 @@ int try_launch_scat_j1(const DtParams& p, cudaStream_t stream);
 int try_launch_fwd_j2plus(const DtParams& p, cudaStream_t stream);
 int try_launch_inv_j1(const DtParams& p, cudaStream_t stream);
 int try_launch_inv_j2plus(const DtParams& p, cudaStream_t stream);
+
+// fused multi-level DWT analysis (k_pyramid.cu): plan_dwt_pyramid fills everything but the output pointers and the
+// taps and returns kNoFastPath when the fused kernel does not apply (then run the levels one by one)
+int plan_dwt_pyramid(PyrParams& p, const float* x, long long xps, int xpitch, int planes, int H, int W, int J, int L,
+                     int mode);
+int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream);
 
 }  // namespace fast
 }  // namespace b200w

@@ -1,0 +1,41 @@
+// k_pyramid.cu -- translation unit of the fused DWT pyramid kernel (dwt_pyramid.cuh, sm_100a)
+#include "dwt_pyramid.cuh"
+
+namespace b200w {
+namespace fast {
+
+static int max_optin_smem() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 227 * 1024;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) {
+      (void)cudaGetLastError();
+      v = 227 * 1024;
+    }
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+int plan_dwt_pyramid(PyrParams& p, const float* x, long long xps, int xpitch, int planes, int H, int W, int J, int L,
+                     int mode) {
+  return plan_pyramid(p, planes, H, W, J, L, mode, xps, xpitch, x, max_optin_smem()) ? kNoFastPath : 0;
+}
+
+int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream) {
+  switch (p.L) {
+    case 2: return launch_pyramid<2>(p, stream);
+    case 4: return launch_pyramid<4>(p, stream);
+    case 6: return launch_pyramid<6>(p, stream);
+    case 8: return launch_pyramid<8>(p, stream);
+    case 10: return launch_pyramid<10>(p, stream);
+    case 12: return launch_pyramid<12>(p, stream);
+    case 16: return launch_pyramid<16>(p, stream);
+    default: return kNoFastPath;
+  }
+}
+
+}  // namespace fast
+}  // namespace b200w

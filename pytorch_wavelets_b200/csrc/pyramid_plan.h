@@ -1,0 +1,147 @@
+// pyramid_plan.h -- host-side planning (and the index rules shared with the device code) of the fused DWT
+// pyramid kernel (dwt_pyramid.cuh): ONE launch computes all J analysis levels of DWTForward
+// (reference dwt/transform2d.py:68-74 = J x AFB2D, dwt/lowlevel.py:336-347) with no inter-level low-pass in HBM.
+//
+// One CTA per plane, warp-specialised dataflow (every arrow is a shared-memory ring guarded by mbarriers):
+//
+//   producer warp --TMA bulk row copies--> input ring --> level-1 warps --ll rows--> ring --> level-2 warps --> ...
+//                                                             |                                  |
+//                                                             +--- band-pass rows --> staging ---+--> writer warp
+//                                                                                      (linear, at the global phase)  --TMA bulk stores--> HBM
+//
+// * level workers: a lane owns NC = 3 adjacent output columns; the pass along W reads the staged rows with 64-bit
+//   LDS, the pass along H runs in a register window (same FMA order as afb2d_stream / the oracle: bit-identical);
+// * rows are handed on in GROUPS = the output rows one worker stage produces (HS rows); stage s of a level
+//   consumes extended rows [s*RS - PL, (s+1)*RS - PL) of its input, RS = 2*HS, PL = L-2;
+// * the band-pass planes of a level are contiguous (Ho*Wo floats), so a group of rows is one contiguous run in
+//   HBM: the workers deposit it in a staging ring laid out at the run's 128-byte phase and the writer flushes it
+//   with cp.async.bulk (16-byte aligned middle) plus at most 3+3 scalar head/tail elements.
+#pragma once
+#include "common.h"
+
+namespace b200w {
+
+constexpr int kPyrMaxLevels = 4;
+constexpr int kPyrNC = 3;      // output columns per lane
+constexpr int kPyrNGO = 2;     // staging groups per level
+constexpr int kPyrNSlot = 4;   // input-ring slots (half a level-1 stage each)
+constexpr int kPyrAuxWarps = 2;  // warp 0 = producer, warp 1 = writer
+
+struct PyrLevel {
+  int H, W, Ho, Wo;             // input / output size of the level
+  int n_stage;                  // worker stages = output groups
+  int warp0, nwarps;            // compute warps [warp0, warp0 + nwarps) of the CTA
+  int in_off, in_pitch, in_rows;  // input ring: float offset in dynamic smem, row pitch (floats), depth (rows)
+  int n_in;                     // barriers per direction on the input ring: slots (level 0) / groups (levels >= 1)
+  int bar_in;                   // index of in_full[0]; in_empty[0] = bar_in + n_in
+  int st_off, st_cap, nbands;   // staging: float offset of band 0, floats per band (multiple of 32), 3 (+1: final ll)
+  int bar_out;                  // index of out_full[0]; out_empty[0] = bar_out + kPyrNGO
+};
+
+struct PyrParams {
+  const float* x; long long xps; int xpitch;
+  float* yl;
+  float* highs[kPyrMaxLevels];
+  int planes, J, mode, L;
+  int zero_off;                 // a row of zeros (floats) for zero-padding rows of levels >= 1
+  int n_bars, smem_bytes, threads;
+  PyrLevel lv[kPyrMaxLevels];
+  Taps fw_lo, fw_hi, fh_lo, fh_hi;
+};
+
+// ---- compile-time shape of a worker stage for filter length L ---------------------------------------------
+constexpr int pyr_hs(int L) {     // half-stages (= output rows) per stage: a multiple of the window period L/2, even, >= 4
+  int m = 1;
+  while ((L / 2) * m < 4 || (((L / 2) * m) & 1)) ++m;
+  return (L / 2) * m;
+}
+constexpr int pyr_halo(int L) { return (L - 2 + 3) / 4 * 4; }   // left pad of a ring row (floats)
+
+// ---- group / stage index rules (host plan simulation and device code use the same functions) -----------------
+// rows of group g of a level with Ho output rows: [g*HS - PRO, (g+1)*HS - PRO) clipped to [0, Ho)
+B200W_HD int pyr_group_end(int g, int HS, int PRO) { return (g + 1) * HS - PRO; }   // exclusive, unclipped
+B200W_HD int pyr_group_of_row(int r, int HS, int PRO) { return (r + PRO) / HS; }
+
+// largest source row stage t of a consumer reads (input height H): rows e in [t*RS - PL, (t+1)*RS - PL) -> ext(e)
+B200W_HD int pyr_stage_max_row(int t, int RS, int PL, int H, int mode) {
+  const int e0 = t * RS - PL, e1 = e0 + RS - 1;
+  int hi = imin(e1, H - 1);
+  if (e0 < 0) {                       // mirrored rows above the image: the most negative one reaches farthest
+    const int g = ext_index(e0, H, mode);
+    if (g > hi) hi = g;
+  }
+  if (hi < 0) hi = 0;
+  return hi;
+}
+// every row below this bound is dead once stage t is done (the bottom mirror reaches back to H - L + 1)
+B200W_HD int pyr_stage_release_bound(int t, int RS, int PL, int H, int L) {
+  return imin((t + 1) * RS - PL, H - L + 1);
+}
+
+// ---- the plan -----------------------------------------------------------------------------------------------
+// Returns 0 and fills p (everything except pointers and taps), or 1 when the fused kernel does not apply.
+inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, int mode, long long xps, int xpitch,
+                        const void* x, int max_smem_bytes) {
+  if (J < 1 || J > kPyrMaxLevels) return 1;
+  if (L < 2 || (L & 1) || L > 16) return 1;
+  if (mode != B200W_MODE_ZERO && mode != B200W_MODE_SYMMETRIC && mode != B200W_MODE_REFLECT) return 1;
+  // TMA bulk row copies: 16-byte aligned source rows of a multiple of 16 bytes
+  if ((W & 3) || (xpitch & 3) || (xps & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
+  const int HS = pyr_hs(L), RS = 2 * HS, PL = L - 2, PRO = PL / 2, HALO = pyr_halo(L);
+  p.planes = planes; p.J = J; p.mode = mode; p.L = L;
+  int warp = kPyrAuxWarps;
+  int h = H, w = W;
+  int nbar = 0;
+  int off = 0;                                   // floats, after the barrier block (added at the end)
+  for (int l = 0; l < J; ++l) {
+    PyrLevel& v = p.lv[l];
+    if (h < L || w < L) return 1;                // one reflection must cover the halo
+    v.H = h; v.W = w;
+    v.Ho = (h + L - 1) / 2; v.Wo = (w + L - 1) / 2;
+    v.n_stage = (v.Ho + PRO + HS - 1) / HS;
+    const int lanes = (v.Wo + kPyrNC - 1) / kPyrNC;
+    v.nwarps = (lanes + 31) / 32;
+    v.warp0 = warp; warp += v.nwarps;
+    // ring row: HALO left pad, the row, right halo; a lane with at least one valid column reads up to
+    // HALO + 2*(c0 + NC - 1) + 1 with c0 <= Wo - 1  ->  pitch >= HALO + 2*(Wo + NC - 2) + 2
+    v.in_pitch = (HALO + 2 * (v.Wo + kPyrNC - 2) + 2 + 3) / 4 * 4;
+    if (v.in_pitch < HALO + w + L - 1) v.in_pitch = (HALO + w + L - 1 + 3) / 4 * 4;
+    if (l == 0) {
+      v.n_in = kPyrNSlot;
+      v.in_rows = kPyrNSlot * HS;
+    } else {
+      // groups of the previous level that must be resident at once: simulate the consumer's stage sequence
+      const PyrLevel& u = p.lv[l - 1];
+      int need = 1, rel = 0;
+      for (int t = 0; t < v.n_stage; ++t) {
+        const int g_need = imin(pyr_group_of_row(pyr_stage_max_row(t, RS, PL, h, mode), HS, PRO), u.n_stage - 1);
+        if (g_need - rel + 1 > need) need = g_need - rel + 1;
+        const int lo = pyr_stage_release_bound(t, RS, PL, h, L);
+        while (rel < u.n_stage && pyr_group_end(rel, HS, PRO) <= lo) ++rel;
+      }
+      v.n_in = need + 1;                         // one more so the producing level can work ahead
+      v.in_rows = v.n_in * HS;
+    }
+    v.in_off = off; off += v.in_rows * v.in_pitch;
+    v.bar_in = nbar; nbar += 2 * v.n_in;
+    v.nbands = (l == J - 1) ? 4 : 3;
+    v.st_cap = (kPyrNGO * HS * v.Wo + 31) / 32 * 32;
+    v.st_off = off; off += v.nbands * v.st_cap;
+    v.bar_out = nbar; nbar += 2 * kPyrNGO;
+    h = v.Ho; w = v.Wo;
+  }
+  int maxpitch = 0;
+  for (int l = 0; l < J; ++l) maxpitch = imax(maxpitch, p.lv[l].in_pitch);
+  p.zero_off = off; off += (maxpitch + 2 * kPyrNC + 8 + 3) / 4 * 4;
+  p.n_bars = nbar;
+  const int bar_floats = (2 * nbar + 31) / 32 * 32;   // 8 bytes each, block rounded to 128 bytes
+  for (int l = 0; l < J; ++l) { p.lv[l].in_off += bar_floats; p.lv[l].st_off += bar_floats; }
+  p.zero_off += bar_floats;
+  p.smem_bytes = (off + bar_floats) * 4;
+  p.threads = 32 * warp;
+  if (p.threads > 512 || p.smem_bytes > max_smem_bytes) return 1;
+  p.x = static_cast<const float*>(x); p.xps = xps; p.xpitch = xpitch;
+  return 0;
+}
+
+}  // namespace b200w

@@ -6,6 +6,8 @@ Mirrors the reference's Function layer (``pytorch_wavelets/dwt/lowlevel.py``: ``
 behaviour -- but every level is ONE fused CUDA kernel behind the C ABI (``b200w_dwt_afb2d`` /
 ``b200w_dwt_sfb2d``) instead of a sequence of ATen convolutions, gathers and copies.
 """
+import ctypes
+
 import numpy as np
 import torch
 from torch.autograd import Function
@@ -155,6 +157,45 @@ def sfb2d_level(ll, highs, gh_lo, gh_hi, gw_lo, gw_hi, mode, out_hw=None):
     return y
 
 
+def dwt_forward_levels(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, J):
+    """All J analysis levels through ONE C-ABI call (``b200w_dwt_forward``): a single fused kernel launch when the
+    pyramid kernel applies (no inter-level low-pass in device memory), one launch per level otherwise.
+    Returns ``(yl (N,C,H_J,W_J), [yh_1 .. yh_J])`` -- contiguous, the reference's return layout."""
+    _ffi.require_cuda_f32(x, 'x')
+    _check_bank_mode(mode)
+    if x.dim() != 4:
+        raise ValueError('expected a 4-D (N,C,H,W) input, got shape {}'.format(tuple(x.shape)))
+    L = _ffi.lib()
+    fw_lo, fw_hi, fh_lo, fh_hi = [_ffi.host_taps(f) for f in (fw_lo, fw_hi, fh_lo, fh_hi)]
+    if fw_lo.n != fw_hi.n or fh_lo.n != fh_hi.n:
+        raise ValueError('low-pass and high-pass filters must have equal length')
+    N, C, H, W = x.shape
+    x, xps, xpitch = _ffi.planes_view(x)
+    sizes = []
+    h, w = H, W
+    for _ in range(J):
+        h, w = L.b200w_dwt_coeff_len(h, fh_lo.n, mode), L.b200w_dwt_coeff_len(w, fw_lo.n, mode)
+        sizes.append((h, w))
+    yh = [x.new_empty((N, C, 3, hh, ww)) for hh, ww in sizes]
+    yl = x.new_empty((N, C) + sizes[-1])
+    if N * C > 0:
+        with torch.cuda.device(x.device):
+            wsb = L.b200w_dwt_forward_workspace(x.data_ptr(), xps, xpitch, N * C, H, W, J, fw_lo.n, fh_lo.n, mode)
+            if wsb < 0:
+                _ffi.check(int(wsb), 'b200w_dwt_forward_workspace')
+            ws = x.new_empty(((wsb + 3) // 4,)) if wsb > 0 else None
+            ptrs = (ctypes.c_void_p * J)(*[t.data_ptr() for t in yh])
+            alg = 4 * N * C * (H * W + 3 * sum(a * b for a, b in sizes) + sizes[-1][0] * sizes[-1][1])
+            tag = ('dwt_pyramid' if wsb == 0 else 'dwt_levels') + ' %dx%d L%d J%d' % (H, W, fw_lo.n, J)
+            with _ffi.span(tag, alg):
+                rc = _ffi.entry('b200w_dwt_forward')(x.data_ptr(), xps, xpitch, N * C, H, W, J, yl.data_ptr(), ptrs,
+                                                     fw_lo.ptr, fw_hi.ptr, fw_lo.n, fh_lo.ptr, fh_hi.ptr, fh_lo.n,
+                                                     mode, None if ws is None else ws.data_ptr(), wsb,
+                                                     _ffi.stream_of(x))
+        _ffi.check(rc, 'b200w_dwt_forward')
+    return yl, yh
+
+
 # ---- autograd Functions (the reference's drop-in boundary) ------------------------------------------------
 
 class AFB2D(Function):
@@ -211,3 +252,35 @@ class SFB2D(Function):
             if not ctx.has_highs:
                 dhigh = None
         return dlow, dhigh, None, None, None, None, None
+
+
+class DWTPyramid(Function):
+    """All J levels of ``DWTForward.forward`` (reference dwt/transform2d.py:68-74) as one differentiable op:
+    ``apply(x, h0_row, h1_row, h0_col, h1_col, mode, J) -> (yl, yh_1, ..., yh_J)`` with the filter arguments of
+    ``AFB2D`` (``*_row`` along W, ``*_col`` along H).  Forward = one fused kernel launch where the pyramid kernel
+    applies; backward = the reference's chain of ``AFB2D.backward`` (synthesis with the stored analysis filters,
+    cropped to each level's input size, dwt/lowlevel.py:350-365)."""
+
+    @staticmethod
+    def forward(ctx, x, h0_row, h1_row, h0_col, h1_col, mode, J):
+        ctx.taps = tuple(_ffi.host_taps(f) for f in (h0_row, h1_row, h0_col, h1_col))
+        mode = int(mode)
+        int_to_mode(mode)
+        ctx.mode = mode
+        yl, yh = dwt_forward_levels(x, *ctx.taps, mode, int(J))
+        ctx.in_shapes = [tuple(x.shape[-2:])] + [tuple(h.shape[-2:]) for h in yh[:-1]]
+        return (yl,) + tuple(yh)
+
+    @staticmethod
+    def backward(ctx, dyl, *dyh):
+        dx = None
+        if ctx.needs_input_grad[0]:
+            h0_row, h1_row, h0_col, h1_col = ctx.taps
+            low = dyl
+            for j in range(len(dyh) - 1, -1, -1):
+                sh = ctx.in_shapes[j]
+                if low is None:
+                    low = dyh[j].new_zeros(dyh[j].shape[:2] + dyh[j].shape[-2:])
+                low = sfb2d_level(low.contiguous(), dyh[j], h0_col, h1_col, h0_row, h1_row, ctx.mode, out_hw=sh)
+            dx = low
+        return dx, None, None, None, None, None, None

@@ -51,18 +51,15 @@ class DWTForward(nn.Module):
         self.mode = mode
 
     def forward(self, x):
-        yh = []
-        ll = x
         mode = lowlevel.mode_to_int(self.mode)
-        for j in range(self.J):
-            # same argument order as reference transform2d.py:70-71: the *_col buffers land on the
-            # Function's h*_row parameters and therefore filter along W; *_row buffers along H.
-            # Intermediate low-passes are internal hand-offs: their row pitch is padded to a 128-byte line so
-            # both the store and the next level's staging are line-aligned; the returned yl is contiguous.
-            ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode,
-                                            j < self.J - 1)
-            yh.append(high)
-        return ll, yh
+        if self.J < 1:
+            return x, []
+        # same argument order as reference transform2d.py:70-71: the *_col buffers land on the Function's
+        # h*_row parameters and therefore filter along W; the *_row buffers filter along H.
+        # The level loop of the reference (:68-74) runs inside ONE C-ABI call: a single fused kernel launch for
+        # all J levels where the pyramid kernel applies, one launch per level otherwise.
+        out = lowlevel.DWTPyramid.apply(x, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode, self.J)
+        return out[0], list(out[1:])
 
 
 class DWTInverse(nn.Module):

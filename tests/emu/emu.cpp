@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../pytorch_wavelets_b200/csrc/launch_params.h"
+#include "../../pytorch_wavelets_b200/csrc/pyramid_plan.h"
 
 using namespace b200w;
 
@@ -102,6 +103,25 @@ int emu_dtcwt_inv_j2plus(const float* ll, long long llps, int llpitch, const flo
   if (rc) return rc;
   run_blocks(p, (long long)N * C * p.tiles_x * p.tiles_y, invj2_smem_floats(m),
              [](const DtParams& q, int b, float* s) { inv_j2plus_tile<NT>(q, b, s); });
+  return 0;
+}
+
+// The shipped host-side plan of the fused pyramid kernel (pyramid_plan.h), flattened for the CPU tests:
+// out = {rc, smem_bytes, threads, n_bars, zero_off, then per level: H, W, Ho, Wo, n_stage, warp0, nwarps, in_off,
+//        in_pitch, in_rows, n_in, bar_in, st_off, st_cap, nbands, bar_out}
+int emu_plan_pyramid(int planes, int H, int W, int J, int L, int mode, int xpitch, int max_smem, int* out) {
+  PyrParams p;
+  memset(&p, 0, sizeof(p));
+  alignas(16) static float dummy[4];
+  const int rc = plan_pyramid(p, planes, H, W, J, L, mode, (long long)H * xpitch, xpitch, dummy, max_smem);
+  out[0] = rc; out[1] = p.smem_bytes; out[2] = p.threads; out[3] = p.n_bars; out[4] = p.zero_off;
+  if (rc) return rc;
+  for (int l = 0; l < J; ++l) {
+    const PyrLevel& v = p.lv[l];
+    const int f[16] = {v.H, v.W, v.Ho, v.Wo, v.n_stage, v.warp0, v.nwarps, v.in_off, v.in_pitch, v.in_rows, v.n_in,
+                       v.bar_in, v.st_off, v.st_cap, v.nbands, v.bar_out};
+    for (int i = 0; i < 16; ++i) out[5 + 16 * l + i] = f[i];
+  }
   return 0;
 }
 

@@ -19,7 +19,7 @@ def lib():
         so = os.path.join(_HERE, 'libb200wave_emu.so')
         srcs = [os.path.join(_HERE, 'emu.cpp')] + [
             os.path.join(_ROOT, 'pytorch_wavelets_b200', 'csrc', f)
-            for f in ('common.h', 'tile_kernels.h', 'launch_params.h')]
+            for f in ('common.h', 'tile_kernels.h', 'launch_params.h', 'pyramid_plan.h')]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(['g++', '-O2', '-fPIC', '-fopenmp', '-ffp-contract=off', '-std=c++17',
                                    '-Wno-unknown-pragmas', '-shared', '-o', so, srcs[0]])
@@ -158,3 +158,19 @@ def scat_j1(x, h0, h1, mode='symmetric', magbias=1e-2, want_grad_aux=False):
                            orc.mode_int(mode), ctypes.c_float(magbias))
     assert rc == 0, rc
     return (z, dre, dim) if want_grad_aux else z
+
+
+PLAN_FIELDS = ('H', 'W', 'Ho', 'Wo', 'n_stage', 'warp0', 'nwarps', 'in_off', 'in_pitch', 'in_rows', 'n_in', 'bar_in',
+               'st_off', 'st_cap', 'nbands', 'bar_out')
+
+
+def plan_pyramid(planes, H, W, J, L, mode, xpitch=None, max_smem=227 * 1024):
+    """The shipped plan of the fused DWT pyramid kernel (pyramid_plan.h) as a dict, or None when it does not apply."""
+    out = (ctypes.c_int * (5 + 16 * 4))()
+    rc = lib().emu_plan_pyramid(planes, H, W, J, L, orc.mode_int(mode), W if xpitch is None else xpitch, max_smem, out)
+    if rc:
+        return None
+    d = {'smem_bytes': out[1], 'threads': out[2], 'n_bars': out[3], 'zero_off': out[4], 'levels': []}
+    for l in range(J):
+        d['levels'].append(dict(zip(PLAN_FIELDS, out[5 + 16 * l: 5 + 16 * (l + 1)])))
+    return d

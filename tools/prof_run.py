@@ -25,6 +25,14 @@ elif which == 'dtcwtinv':
     c = pw.DTCWTForward(J=3).to(dev)(x)
     g = pw.DTCWTInverse().to(dev)
     f = lambda _: g(c)
+elif which == 'c5':
+    x = torch.randn(n, 16, 2048, 2048, device=dev)
+    f = pw.DWTForward(J=4, wave='db8', mode='zero').to(dev)
+elif which == 'c5inv':
+    x = torch.randn(n, 16, 2048, 2048, device=dev)
+    c = pw.DWTForward(J=4, wave='db8', mode='zero').to(dev)(x)
+    g = pw.DWTInverse(wave='db8', mode='zero').to(dev)
+    f = lambda _: g(c)
 elif which == 'scat':
     x = torch.randn(n, 3, 256, 256, device=dev)
     f = torch.nn.Sequential(pw.ScatLayer(), pw.ScatLayer()).to(dev)
