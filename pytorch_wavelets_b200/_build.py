@@ -59,10 +59,11 @@ def _run(cmd):
     return r.stdout
 
 
-def build(force=False, verbose=False, out=None, extra_flags=()):
+def build(force=False, verbose=False, out=None, extra_flags=(), only=None):
     """Compile every translation unit of csrc/ (in parallel, one nvcc per .cu, objects cached under build/) and link
     libb200wave.so.  ``out`` / ``extra_flags`` build an experimental variant next to the default one (objects are
-    then not cached); the package only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
+    then not cached); ``only`` = the translation units the extra flags apply to (the rest link from the cache).
+    The package only ever loads libb200wave.so unless B200W_LIB points elsewhere."""
     from concurrent.futures import ThreadPoolExecutor
     target = out or SO
     if out is None and not force and not needs_build():
@@ -70,16 +71,18 @@ def build(force=False, verbose=False, out=None, extra_flags=()):
     variant = out is not None or bool(extra_flags)
     objdir = os.path.join(OBJ, 'variant_%d' % os.getpid()) if variant else OBJ
     os.makedirs(objdir, exist_ok=True)
+    os.makedirs(OBJ, exist_ok=True)
     hdr_t = _newest_header()
     jobs = []
     objs = []
     for src in sources():
-        o = os.path.join(objdir, src[:-3] + '.o')
+        special = variant and (only is None or src in only)
+        o = os.path.join(objdir if special else OBJ, src[:-3] + '.o')
         objs.append(o)
         sp = os.path.join(CSRC, src)
-        if force or variant or not os.path.exists(o) or os.path.getmtime(o) < max(hdr_t, os.path.getmtime(sp)):
-            jobs.append([nvcc()] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) +
-                        ['-c', '-o', o, sp])
+        if force or special or not os.path.exists(o) or os.path.getmtime(o) < max(hdr_t, os.path.getmtime(sp)):
+            jobs.append([nvcc()] + NVCC_FLAGS + (list(extra_flags) if special else []) +
+                        (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', o, sp])
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
         logs = list(ex.map(_run, jobs))
     log = _run([nvcc()] + LINK_FLAGS + ['-o', target] + objs)

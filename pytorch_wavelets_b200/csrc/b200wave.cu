@@ -292,9 +292,12 @@ static int dwt_forward_impl(const float* x, long long x_plane_stride, int x_pitc
     PyrParams pp;
     if (fast::plan_dwt_pyramid(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, mode) == 0) {
       int rc;
-      if ((rc = set_taps(pp.fw_lo, fw_lo, Lw)) || (rc = set_taps(pp.fw_hi, fw_hi, Lw)) ||
-          (rc = set_taps(pp.fh_lo, fh_lo, Lh)) || (rc = set_taps(pp.fh_hi, fh_hi, Lh)))
-        return rc;
+      if (!fw_lo || !fw_hi || !fh_lo || !fh_hi) return B200W_EARG;
+      for (int i = 0; i < kPyrMaxTaps; ++i) {
+        const bool on = i < Lw;
+        pp.fw[2 * i] = on ? fw_lo[i] : 0.f; pp.fw[2 * i + 1] = on ? fw_hi[i] : 0.f;
+        pp.fh_lo[i] = on ? fh_lo[i] : 0.f; pp.fh_hi[i] = on ? fh_hi[i] : 0.f;
+      }
       pp.yl = yl;
       for (int j = 0; j < kPyrMaxLevels; ++j) pp.highs[j] = (j < J) ? highs[j] : nullptr;
       rc = fast::launch_dwt_pyramid(pp, (cudaStream_t)stream);

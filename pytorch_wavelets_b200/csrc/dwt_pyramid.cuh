@@ -13,6 +13,25 @@
 namespace b200w {
 namespace fast {
 
+// ---- optional wait-time instrumentation (variant builds only: -DB200W_PYR_PROF) -----------------------------------
+#ifdef B200W_PYR_PROF
+__device__ unsigned long long g_pyr_prof[64];   // [role (0 producer, 1 writer, 2 + level)][8 counters]
+#define PYR_T0() const long long pyr_t0_ = clock64()
+#define PYR_ACC(k) prof[k] += (unsigned long long)(clock64() - pyr_t0_)
+#define PYR_DECL() unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long pyr_life_ = clock64()
+#define PYR_FLUSH(role, lane)                                                                              \
+  do {                                                                                                     \
+    prof[7] = (unsigned long long)(clock64() - pyr_life_);                                                 \
+    if ((lane) == 0)                                                                                       \
+      for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_pyr_prof[8 * (role) + k_], prof[k_]);                    \
+  } while (0)
+#else
+#define PYR_T0() do {} while (0)
+#define PYR_ACC(k) do {} while (0)
+#define PYR_DECL() do {} while (0)
+#define PYR_FLUSH(role, lane) do {} while (0)
+#endif
+
 template <int L>
 struct PyrCfg {
   static constexpr int NC = kPyrNC;
@@ -54,9 +73,10 @@ __device__ __forceinline__ void bulk_load_g2s(unsigned sdst, const float* gsrc, 
                : "memory");
 }
 
-// 128-byte phase (in floats) of a band's first element in global memory: staging index = (position + phase) % cap
+// 16-byte phase (in floats) of a band's first element in global memory: staging index = (position + phase) % cap, so
+// 16-byte aligned runs in global memory are 16-byte aligned in the staging ring (what the bulk copies need)
 __device__ __forceinline__ int pyr_phase(const float* band_base) {
-  return (int)((reinterpret_cast<uintptr_t>(band_base) >> 2) & 31);
+  return (int)((reinterpret_cast<uintptr_t>(band_base) >> 2) & 3);
 }
 // global base of band b of level l for this plane (b == 3: the final low-pass)
 __device__ __forceinline__ float* pyr_band_base(const PyrParams& p, int l, int b, int plane) {
@@ -78,11 +98,12 @@ __device__ __forceinline__ void pyr_producer(const PyrParams& p, int plane, floa
   const unsigned row_bytes = (unsigned)v.W * 4u;
   float* ring = smem + v.in_off;
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+  PYR_DECL();
 #pragma unroll 1
   for (int q = 0; q < n_slots; ++q) {
     const int slot = q % kPyrNSlot;
     const int use = q / kPyrNSlot;
-    if (use > 0) mbar_wait(bar0 + 8 * (v.bar_in + v.n_in + slot), (unsigned)((use - 1) & 1));
+    if (use > 0) { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_in + v.n_in + slot), (unsigned)((use - 1) & 1)); PYR_ACC(0); }
     // row j of the slot holds extended row e = q*HS + j - PL
     int src = -1;
     if (lane < C::HS) src = ext_index(q * C::HS + lane - C::PL, v.H, p.mode);
@@ -102,6 +123,7 @@ __device__ __forceinline__ void pyr_producer(const PyrParams& p, int plane, floa
       bulk_load_g2s(ring_s + 4u * (unsigned)((slot * C::HS + lane) * v.in_pitch + C::HALO),
                     src_plane + (long long)src * p.xpitch, row_bytes, full);
   }
+  PYR_FLUSH(0, lane);
 }
 
 // ================================================================================================
@@ -117,6 +139,7 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
   int remaining = 0;
   for (int l = 0; l < p.J; ++l) remaining += p.lv[l].n_stage;
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+  PYR_DECL();
 
   while (remaining > 0) {
     bool any = false;
@@ -128,6 +151,7 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
       if (g >= v.n_stage) continue;
       if (!__all_sync(0xffffffffu, mbar_test(bar0 + 8 * (v.bar_out + g % kPyrNGO), (unsigned)((g / kPyrNGO) & 1)))) continue;
       any = true;
+      PYR_T0();
       // rows [k0, k1) of the level = stream positions [s0, s1) of every band
       const int k0 = imax(0, g * C::HS - C::PRO), k1 = imin(v.Ho, (g + 1) * C::HS - C::PRO);
       const int s0 = k0 * v.Wo, s1 = k1 * v.Wo;
@@ -164,10 +188,16 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
       prev_l = l; prev_g = g;
       next_g[l] = g + 1;
       --remaining;
+      PYR_ACC(0);   // time spent flushing events
+#ifdef B200W_PYR_PROF
+      prof[1] += 1;
+#endif
     }
     if (!any) {
       if (prev_l >= 0) {
+        PYR_T0();
         bulk_wait_read<0>();
+        PYR_ACC(2);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (p.lv[prev_l].bar_out + kPyrNGO + prev_g % kPyrNGO));
         prev_l = -1;
@@ -176,120 +206,164 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
       }
     }
   }
-  bulk_wait<0>();   // all bulk stores of this plane are complete before the CTA retires
+  { PYR_T0(); bulk_wait<0>(); PYR_ACC(3); }   // all bulk stores of this plane are complete before the CTA retires
+  PYR_FLUSH(1, lane);
 }
 
 // ================================================================================================
 // level worker
 // ================================================================================================
+// Shared-memory accesses of the hot loop are volatile asm on shared-window addresses: they keep their program order
+// relative to the mbarrier waits / arrives (also volatile asm), and the compiler never has to prove an address is shared.
+__device__ __forceinline__ float2 lds64_s(unsigned s) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(s));
+  return v;
+}
+// ... with a compile-time byte offset folded into the instruction (no address arithmetic per access)
+template <int OFF>
+__device__ __forceinline__ float2 lds64_so(unsigned s) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];\n" : "=f"(v.x), "=f"(v.y) : "r"(s), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_so(unsigned s, float v) {
+  asm volatile("st.shared.f32 [%0+%2], %1;\n" ::"r"(s), "f"(v), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ uint2 lds64u_s(unsigned s) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(s));
+  return v;
+}
+__device__ __forceinline__ void stsu_s(unsigned s, unsigned v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(s), "r"(v) : "memory"); }
+
 template <int L>
-__device__ __forceinline__ void pyr_rowpass(const PyrParams& p, const float* row, float2 (&dst)[PyrCfg<L>::NC]) {
+__device__ __forceinline__ void pyr_rowpass(const PyrParams& p, unsigned row_s, float2 (&dst)[PyrCfg<L>::NC]) {
   using C = PyrCfg<L>;
   float x[C::NX];
-#pragma unroll
-  for (int q = 0; q < C::NX / 2; ++q) {
-    const float2 v = *reinterpret_cast<const float2*>(row + 2 * q);
-    x[2 * q] = v.x; x[2 * q + 1] = v.y;
+  {
+    float2 v;
+#define PYR_LD(Q) if constexpr (Q < C::NX / 2) { v = lds64_so<8 * (Q)>(row_s); x[2 * (Q)] = v.x; x[2 * (Q) + 1] = v.y; }
+    PYR_LD(0) PYR_LD(1) PYR_LD(2) PYR_LD(3) PYR_LD(4) PYR_LD(5) PYR_LD(6) PYR_LD(7) PYR_LD(8) PYR_LD(9) PYR_LD(10) PYR_LD(11)
+#undef PYR_LD
+    static_assert(C::NX / 2 <= 12, "unrolled loads");
   }
 #pragma unroll
   for (int o = 0; o < C::NC; ++o) {
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < L; ++j) r = ffma2_s(x[2 * o + j], make_float2(p.fw_lo.t[j], p.fw_hi.t[j]), r);
+    for (int j = 0; j < L; ++j) r = ffma2_s(x[2 * o + j], make_float2(p.fw[2 * j], p.fw[2 * j + 1]), r);
     dst[o] = r;
   }
 }
 
+// Where the finished rows of one lane go.  Staging: band b's ring holds R = kPyrNGO * HS rows; row k sits at row slot
+// k % R, shifted by the band's global 128-byte phase, so only the last slot's tail wraps to the ring start.
 template <int L>
-struct PyrEmit {   // where the finished rows of one lane go
+struct PyrEmit {
   unsigned st_s[4];     // staging band bases (shared-window byte addresses)
-  int sidx[4];          // staging float index of (current row, c0) per band
-  int cap, Wo, nv, c0, nb;
+  unsigned so[4];       // byte offset of (current row slot, c0) inside the band's ring, phase included
+  unsigned capb, wob;   // ring size and row advance in bytes
+  int nv, nb, kslot, R;
   unsigned nr_s;        // next level's ring: byte address of (row 0, column c0); 0 for the last level
-  int nr_pitch4, nr_rows, nr_slot;   // pitch in bytes, ring depth, slot of the current row
-  int Wn, mode;         // next level's input width (= Wo), extension mode (for the halo copies)
-  bool edge;
+  unsigned nr_off, nr_pitch4, nr_bytes;   // byte offset of the current row, row pitch, ring size
+  int dup[kPyrNC];      // byte delta from a column's cell to the halo cell the extension maps onto it (0: none)
 
-  __device__ __forceinline__ void put(int b, int i, float v) const {
-    int e = sidx[b] + i;
-    if (e >= cap) e -= cap;
-    sts_s(st_s[b] + 4u * (unsigned)e, v);
+  __device__ __forceinline__ void putn(int b, const float (&v)[kPyrNC], bool wrap_slot) {
+    const unsigned a = st_s[b] + so[b];
+    if (!wrap_slot) {
+      if (nv > 0) sts_so<0>(a, v[0]);
+      if (nv > 1) sts_so<4>(a, v[1]);
+      if constexpr (kPyrNC > 2) { if (nv > 2) sts_so<8>(a, v[kPyrNC > 2 ? 2 : 0]); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kPyrNC; ++i) {
+        unsigned oi = so[b] + 4u * i;
+        if (oi >= capb) oi -= capb;
+        if (nv > i) sts_s(st_s[b] + oi, v[i]);
+      }
+    }
   }
   // lo[o] = {ll, hl}, hi[o] = {lh, hh} of column c0 + o
   __device__ __forceinline__ void row(const float2 (&lo)[kPyrNC], const float2 (&hi)[kPyrNC]) {
-    using C = PyrCfg<L>;
+    float v0[kPyrNC], v1[kPyrNC], v2[kPyrNC], v3[kPyrNC];
 #pragma unroll
-    for (int o = 0; o < kPyrNC; ++o) {
-      if (o < nv) {
-        put(0, o, hi[o].x);
-        put(1, o, lo[o].y);
-        put(2, o, hi[o].y);
-        if (nb == 4) put(3, o, lo[o].x);
-      }
-    }
+    for (int i = 0; i < kPyrNC; ++i) { v0[i] = hi[i].x; v1[i] = lo[i].y; v2[i] = hi[i].y; v3[i] = lo[i].x; }
+    const bool wrap_slot = (kslot == R - 1);
+    putn(0, v0, wrap_slot);
+    putn(1, v1, wrap_slot);
+    putn(2, v2, wrap_slot);
+    if (nb == 4) putn(3, v3, wrap_slot);
+    const unsigned back = wrap_slot ? capb : 0u;   // the slot after the last one is slot 0
+#pragma unroll
+    for (int b = 0; b < 4; ++b) so[b] = so[b] + wob - back;
+    kslot = wrap_slot ? 0 : kslot + 1;
     if (nr_s != 0) {
-      const unsigned rb = nr_s + (unsigned)(nr_slot * nr_pitch4);
+      const unsigned rb = nr_s + nr_off;
+      if (nv > 0) sts_so<0>(rb, v3[0]);
+      if (nv > 1) sts_so<4>(rb, v3[1]);
+      if constexpr (kPyrNC > 2) { if (nv > 2) sts_so<8>(rb, v3[kPyrNC > 2 ? 2 : 0]); }
 #pragma unroll
-      for (int o = 0; o < kPyrNC; ++o)
-        if (o < nv) sts_s(rb + 4u * o, lo[o].x);
-      if (edge) {   // copies into the halo cells the extension maps onto this column (next level's W-pass border)
-#pragma unroll
-        for (int o = 0; o < kPyrNC; ++o) {
-          if (o < nv) {
-            const int c = c0 + o;
-            if (mode == B200W_MODE_SYMMETRIC) {
-              if (c < C::PL) sts_s(rb + 4u * o - 4u * (unsigned)(2 * c + 1), lo[o].x);             // cell -1-c
-              if (c >= Wn - (L - 1)) sts_s(rb + 4u * o + 4u * (unsigned)(2 * (Wn - c) - 1), lo[o].x);  // cell 2Wn-1-c
-            } else if (mode == B200W_MODE_REFLECT) {
-              if (c >= 1 && c <= C::PL) sts_s(rb + 4u * o - 4u * (unsigned)(2 * c), lo[o].x);        // cell -c
-              if (c <= Wn - 2 && c >= Wn - L) sts_s(rb + 4u * o + 4u * (unsigned)(2 * (Wn - 1 - c)), lo[o].x);  // 2Wn-2-c
-            }
-          }
-        }
-      }
-      nr_slot = (nr_slot + 1 == nr_rows) ? 0 : nr_slot + 1;
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      sidx[b] += Wo;
-      if (sidx[b] >= cap) sidx[b] -= cap;
+      for (int i = 0; i < kPyrNC; ++i)
+        if (dup[i] != 0) sts_s(rb + 4u * i + (unsigned)dup[i], v3[i]);   // the W-pass border of the next level
+      nr_off += nr_pitch4;
+      if (nr_off >= nr_bytes) nr_off = 0;
     }
   }
 };
 
 template <int L>
-__device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lvl, int wl, int lane, float* smem,
-                                           unsigned bar0) {
+__device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lvl, int wl, int warp, int lane,
+                                           float* smem, unsigned bar0) {
   using C = PyrCfg<L>;
   const PyrLevel& v = p.lv[lvl];
   const bool last = (lvl == p.J - 1);
   const int c0 = C::NC * (32 * wl + lane);
   const int nv = imax(0, imin(C::NC, v.Wo - c0));
-  const int rd = (nv > 0) ? (C::HALO + 2 * c0 - C::PL) : C::HALO;   // lane's read offset inside a ring row
-  const float* in_ring = smem + v.in_off;
-  const float* zero_row = smem + p.zero_off;
+  const unsigned rd4 = 4u * (unsigned)((nv > 0) ? (C::HALO + 2 * c0 - C::PL) : C::HALO);   // read offset in a ring row
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned ring_s = smem_s + 4u * (unsigned)v.in_off;
+  const unsigned zero_s = smem_s + 4u * (unsigned)p.zero_off;
+  const unsigned tab_s = smem_s + 4u * (unsigned)(p.tab_off + 32 * warp);   // this warp's row-address table
 
   PyrEmit<L> em;
-  em.cap = v.st_cap; em.Wo = v.Wo; em.nv = nv; em.c0 = c0; em.nb = v.nbands; em.mode = p.mode;
+  em.capb = 4u * (unsigned)v.st_cap; em.wob = 4u * (unsigned)v.Wo; em.nv = nv; em.nb = v.nbands;
+  em.kslot = 0; em.R = kPyrNGO * C::HS;
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     em.st_s[b] = smem_s + 4u * (unsigned)(v.st_off + (b < v.nbands ? b : 0) * v.st_cap);
-    em.sidx[b] = (b < v.nbands) ? (c0 + pyr_phase(pyr_band_base(p, lvl, b, plane))) % v.st_cap : 0;
+    em.so[b] = (b < v.nbands) ? 4u * (unsigned)(c0 + pyr_phase(pyr_band_base(p, lvl, b, plane))) : 0u;
   }
-  em.nr_s = 0; em.nr_pitch4 = 0; em.nr_rows = 1; em.nr_slot = 0; em.Wn = v.Wo; em.edge = false;
-  int nx_bar = 0, nx_n = 1, nx_warps_first = 0;
+  em.nr_s = 0; em.nr_off = 0; em.nr_pitch4 = 0; em.nr_bytes = 1;
+#pragma unroll
+  for (int i = 0; i < C::NC; ++i) em.dup[i] = 0;
+  int nx_bar = 0, nx_n = 1;
   if (!last) {
     const PyrLevel& u = p.lv[lvl + 1];
     em.nr_s = smem_s + 4u * (unsigned)(u.in_off + C::HALO + c0);
-    em.nr_pitch4 = 4 * u.in_pitch;
-    em.nr_rows = u.in_rows;
-    // this warp's columns map onto halo cells if they touch either end of the row
-    const int cw0 = C::NC * 32 * wl, cw1 = imin(cw0 + C::NC * 32, v.Wo);
-    em.edge = (p.mode != B200W_MODE_ZERO) && (cw0 <= C::PL || cw1 > v.Wo - L);
+    em.nr_pitch4 = 4u * (unsigned)u.in_pitch;
+    em.nr_bytes = em.nr_pitch4 * (unsigned)u.in_rows;
     nx_bar = u.bar_in; nx_n = u.n_in;
+    // halo cells of the next level's rows that the extension maps onto this lane's columns (the plan guarantees
+    // Wo >= 2L - 2, so a column feeds at most one halo cell)
+    const int Wn = v.Wo;
+#pragma unroll
+    for (int i = 0; i < C::NC; ++i) {
+      const int c = c0 + i;
+      int cell = c;   // target cell index (column coordinates); == c means none
+      if (i < nv) {
+        if (p.mode == B200W_MODE_SYMMETRIC) {
+          if (c < C::PL) cell = -1 - c;
+          else if (c >= Wn - (L - 1)) cell = 2 * Wn - 1 - c;
+        } else if (p.mode == B200W_MODE_REFLECT) {
+          if (c >= 1 && c <= C::PL) cell = -c;
+          else if (c <= Wn - 2 && c >= Wn - L) cell = 2 * Wn - 2 - c;
+        }
+      }
+      em.dup[i] = 4 * (cell - c);
+    }
   }
-  (void)nx_warps_first;
   // level 0: does this warp read the left / right halo cells of the staged input rows?
   const int cw0 = C::NC * 32 * wl, cw1 = imin(cw0 + C::NC * 32, v.Wo);
   const bool patch_l = (lvl == 0) && (p.mode != B200W_MODE_ZERO) && (2 * cw0 - C::PL < 0);
@@ -313,24 +387,42 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
 #pragma unroll
     for (int o = 0; o < C::NC; ++o) w[j][o] = make_float2(0.f, 0.f);
 
+  PYR_DECL();
   int g_seen = 0, g_rel = 0;   // levels >= 1: input groups waited for / released so far
   const int prev_stages = (lvl > 0) ? p.lv[lvl - 1].n_stage : 0;
+  const int pitch4 = 4 * v.in_pitch;
 
 #pragma unroll 1
   for (int t = 0; t < v.n_stage; ++t) {
+    // ---- the stage's RS row addresses, one per lane, into this warp's table ----------------------------------
+    if (lane < C::RS) {
+      unsigned a;
+      if (lvl == 0) {
+        const int slot = (2 * t + (lane >= C::HS ? 1 : 0)) % kPyrNSlot;
+        a = ring_s + (unsigned)((slot * C::HS + (lane >= C::HS ? lane - C::HS : lane)) * pitch4);
+      } else {
+        const int e = t * C::RS + lane - C::PL;
+        const int src = ((unsigned)e < (unsigned)v.H) ? e : ext_index_cold(e, v.H, p.mode);
+        a = (src >= 0) ? ring_s + (unsigned)((src % v.in_rows) * pitch4) : zero_s;
+      }
+      stsu_s(tab_s + 4u * lane, a);
+    }
     // ---- room for this stage's output group ---------------------------------------------------------------
-    if (t >= kPyrNGO) mbar_wait(bar0 + 8 * (v.bar_out + kPyrNGO + t % kPyrNGO), (unsigned)((t / kPyrNGO - 1) & 1));
-    if (!last && t >= nx_n) mbar_wait(bar0 + 8 * (nx_bar + nx_n + t % nx_n), (unsigned)((t / nx_n - 1) & 1));
+    if (t >= kPyrNGO) { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_out + kPyrNGO + t % kPyrNGO), (unsigned)((t / kPyrNGO - 1) & 1)); PYR_ACC(1); }
+    if (!last && t >= nx_n) { PYR_T0(); mbar_wait(bar0 + 8 * (nx_bar + nx_n + t % nx_n), (unsigned)((t / nx_n - 1) & 1)); PYR_ACC(2); }
     // ---- inputs ----------------------------------------------------------------------------------------------
-    const float* slot_rows = nullptr;   // level 0: first row of the current input slot
     if (lvl > 0) {
       const int g_need = imin(pyr_group_of_row(pyr_stage_max_row(t, C::RS, C::PL, v.H, p.mode), C::HS, C::PRO),
                               prev_stages - 1);
+      PYR_T0();
       while (g_seen <= g_need) {
         mbar_wait(bar0 + 8 * (v.bar_in + g_seen % v.n_in), (unsigned)((g_seen / v.n_in) & 1));
         ++g_seen;
       }
+      PYR_ACC(0);
     }
+    __syncwarp();   // the table
+    const int k_first = t * C::HS - C::PRO;
 #pragma unroll
     for (int hh = 0; hh < C::HS; ++hh) {
       if (lvl == 0 && (hh == 0 || hh == C::HS / 2)) {
@@ -340,51 +432,49 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
           if (lane == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (q - 1) % kPyrNSlot));
         }
         const int slot = q % kPyrNSlot;
-        mbar_wait(bar0 + 8 * (v.bar_in + slot), (unsigned)((q / kPyrNSlot) & 1));
-        slot_rows = in_ring + slot * C::HS * v.in_pitch;
+        { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_in + slot), (unsigned)((q / kPyrNSlot) & 1)); PYR_ACC(0); }
         if (do_patch) {
+          PYR_T0();
           if (patch_dst >= 0) {
-            const unsigned a = (unsigned)__cvta_generic_to_shared(slot_rows);
+            const unsigned a = ring_s + (unsigned)(slot * C::HS * pitch4);
 #pragma unroll
             for (int j = 0; j < C::HS; ++j)
-              sts_s(a + 4u * (unsigned)(j * v.in_pitch + patch_dst), lds_s(a + 4u * (unsigned)(j * v.in_pitch + patch_src)));
+              sts_s(a + (unsigned)(j * pitch4 + 4 * patch_dst), lds_s(a + (unsigned)(j * pitch4 + 4 * patch_src)));
           }
           __syncwarp();
+          PYR_ACC(4);
         }
       }
-      const float *r0, *r1;
-      if (lvl == 0) {
-        const int j = 2 * hh - ((hh >= C::HS / 2) ? C::HS : 0);
-        r0 = slot_rows + j * v.in_pitch + rd;
-        r1 = r0 + v.in_pitch;
-      } else {
-        const int e = t * C::RS + 2 * hh - C::PL;
-        const int s0 = ((unsigned)e < (unsigned)v.H) ? e : ext_index_cold(e, v.H, p.mode);
-        const int s1 = ((unsigned)(e + 1) < (unsigned)v.H) ? e + 1 : ext_index_cold(e + 1, v.H, p.mode);
-        r0 = (s0 >= 0 ? in_ring + (s0 % v.in_rows) * v.in_pitch : zero_row) + rd;
-        r1 = (s1 >= 0 ? in_ring + (s1 % v.in_rows) * v.in_pitch : zero_row) + rd;
-      }
-      pyr_rowpass<L>(p, r0, w[(2 * hh) % L]);
-      pyr_rowpass<L>(p, r1, w[(2 * hh + 1) % L]);
-      const int k = t * C::HS + hh - C::PRO;
+      const uint2 ra = lds64u_s(tab_s + 8u * hh);
+      pyr_rowpass<L>(p, ra.x + rd4, w[(2 * hh) % L]);
+      pyr_rowpass<L>(p, ra.y + rd4, w[(2 * hh + 1) % L]);
+      const int k = k_first + hh;
       if (k >= 0 && k < v.Ho) {
+        PYR_T0();
         float2 lo[C::NC], hi[C::NC];
 #pragma unroll
         for (int o = 0; o < C::NC; ++o) {
           float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < L; ++j) {
-            a0 = ffma2_s(p.fh_lo.t[j], w[(2 * hh + 2 + j) % L][o], a0);
-            a1 = ffma2_s(p.fh_hi.t[j], w[(2 * hh + 2 + j) % L][o], a1);
+            a0 = ffma2_s(p.fh_lo[j], w[(2 * hh + 2 + j) % L][o], a0);
+            a1 = ffma2_s(p.fh_hi[j], w[(2 * hh + 2 + j) % L][o], a1);
           }
           lo[o] = a0; hi[o] = a1;
         }
         em.row(lo, hi);
+        PYR_ACC(5);
       }
     }
     // ---- hand the inputs back, publish the outputs -----------------------------------------------------------
+#ifdef B200W_PYR_PROF
+    const long long pyr_tf_ = clock64();
+#endif
     fence_proxy_async();   // this lane's staging stores become visible to the bulk-store engine
     __syncwarp();
+#ifdef B200W_PYR_PROF
+    prof[3] += (unsigned long long)(clock64() - pyr_tf_);
+#endif
     if (lane == 0) {
       if (lvl == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (2 * t + 1) % kPyrNSlot));
       mbar_arrive(bar0 + 8 * (v.bar_out + t % kPyrNGO));
@@ -398,6 +488,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
       }
     }
   }
+  PYR_FLUSH(2 + lvl, lane);
 }
 
 // ================================================================================================
@@ -444,9 +535,11 @@ __global__ void __launch_bounds__(MAXT, MINB) dwt_pyramid(const __grid_constant_
 #pragma unroll
     for (int l = 1; l < kPyrMaxLevels; ++l)
       if (l < p.J && warp >= p.lv[l].warp0) lvl = l;
-    pyr_worker<L>(p, plane, lvl, warp - p.lv[lvl].warp0, lane, smem, bar0);
+    pyr_worker<L>(p, plane, lvl, warp - p.lv[lvl].warp0, warp, lane, smem, bar0);
   }
 }
+
+constexpr int kPyrSmallThreads = (kPyrNC >= 3) ? 256 : 384;   // largest CTA that still runs two per SM
 
 template <int L>
 inline int launch_pyramid(const PyrParams& p, cudaStream_t stream) {
@@ -454,14 +547,14 @@ inline int launch_pyramid(const PyrParams& p, cudaStream_t stream) {
   static int smem_set[64] = {};
   int dev = 0;
   (void)cudaGetDevice(&dev);
-  const bool small = p.threads <= 256;
+  const bool small = p.threads <= kPyrSmallThreads;
   if (dev < 0 || dev >= 64 || !(smem_set[dev] & (small ? 1 : 2))) {
-    cudaError_t e = small ? cudaFuncSetAttribute(dwt_pyramid<L, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+    cudaError_t e = small ? cudaFuncSetAttribute(dwt_pyramid<L, kPyrSmallThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
                           : cudaFuncSetAttribute(dwt_pyramid<L, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return kNoFastPath; }
     if (dev >= 0 && dev < 64) smem_set[dev] |= (small ? 1 : 2);
   }
-  if (small) dwt_pyramid<L, 256, 2><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
+  if (small) dwt_pyramid<L, kPyrSmallThreads, 2><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
   else dwt_pyramid<L, 512, 1><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
   return 0;
 }

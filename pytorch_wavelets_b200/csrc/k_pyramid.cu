@@ -39,3 +39,14 @@ int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream) {
 
 }  // namespace fast
 }  // namespace b200w
+
+#ifdef B200W_PYR_PROF
+// variant builds only (tools/pyr_prof.py): read and clear the wait-time counters of dwt_pyramid
+extern "C" int b200w_debug_pyr_prof(unsigned long long* out) {
+  unsigned long long z[64] = {};
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, b200w::fast::g_pyr_prof, sizeof(z)) != cudaSuccess) return -2;
+  if (cudaMemcpyToSymbol(b200w::fast::g_pyr_prof, z, sizeof(z)) != cudaSuccess) return -3;
+  return 0;
+}
+#endif

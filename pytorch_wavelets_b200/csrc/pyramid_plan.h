@@ -22,7 +22,11 @@
 namespace b200w {
 
 constexpr int kPyrMaxLevels = 4;
-constexpr int kPyrNC = 3;      // output columns per lane
+constexpr int kPyrMaxTaps = 16;
+#ifndef B200W_PYR_NC
+#define B200W_PYR_NC 3
+#endif
+constexpr int kPyrNC = B200W_PYR_NC;      // output columns per lane
 constexpr int kPyrNGO = 2;     // staging groups per level
 constexpr int kPyrNSlot = 4;   // input-ring slots (half a level-1 stage each)
 constexpr int kPyrAuxWarps = 2;  // warp 0 = producer, warp 1 = writer
@@ -44,9 +48,14 @@ struct PyrParams {
   float* highs[kPyrMaxLevels];
   int planes, J, mode, L;
   int zero_off;                 // a row of zeros (floats) for zero-padding rows of levels >= 1
+  int tab_off;                  // per-warp tables of the current stage's row addresses (32 words per warp)
   int n_bars, smem_bytes, threads;
   PyrLevel lv[kPyrMaxLevels];
-  Taps fw_lo, fw_hi, fh_lo, fh_hi;
+  // taps: the W-pass pairs {low-pass, high-pass} interleaved (one 64-bit uniform load feeds a packed FMA), the
+  // H-pass taps as two scalar arrays
+  alignas(16) float fw[2 * kPyrMaxTaps];
+  alignas(16) float fh_lo[kPyrMaxTaps];
+  alignas(16) float fh_hi[kPyrMaxTaps];
 };
 
 // ---- compile-time shape of a worker stage for filter length L ---------------------------------------------
@@ -96,6 +105,7 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
   for (int l = 0; l < J; ++l) {
     PyrLevel& v = p.lv[l];
     if (h < L || w < L) return 1;                // one reflection must cover the halo
+    if (l > 0 && w < 2 * L - 2) return 1;        // ... and a column feeds at most one halo cell of the next level
     v.H = h; v.W = w;
     v.Ho = (h + L - 1) / 2; v.Wo = (w + L - 1) / 2;
     v.n_stage = (v.Ho + PRO + HS - 1) / HS;
@@ -125,18 +135,21 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
     v.in_off = off; off += v.in_rows * v.in_pitch;
     v.bar_in = nbar; nbar += 2 * v.n_in;
     v.nbands = (l == J - 1) ? 4 : 3;
-    v.st_cap = (kPyrNGO * HS * v.Wo + 31) / 32 * 32;
+    v.st_cap = kPyrNGO * HS * v.Wo;              // whole rows (a multiple of 4 floats: kPyrNGO * HS % 4 == 0)
     v.st_off = off; off += v.nbands * v.st_cap;
+    off = (off + 3) / 4 * 4;
     v.bar_out = nbar; nbar += 2 * kPyrNGO;
     h = v.Ho; w = v.Wo;
   }
   int maxpitch = 0;
   for (int l = 0; l < J; ++l) maxpitch = imax(maxpitch, p.lv[l].in_pitch);
   p.zero_off = off; off += (maxpitch + 2 * kPyrNC + 8 + 3) / 4 * 4;
+  p.tab_off = off; off += 32 * warp;
   p.n_bars = nbar;
   const int bar_floats = (2 * nbar + 31) / 32 * 32;   // 8 bytes each, block rounded to 128 bytes
   for (int l = 0; l < J; ++l) { p.lv[l].in_off += bar_floats; p.lv[l].st_off += bar_floats; }
   p.zero_off += bar_floats;
+  p.tab_off += bar_floats;
   p.smem_bytes = (off + bar_floats) * 4;
   p.threads = 32 * warp;
   if (p.threads > 512 || p.smem_bytes > max_smem_bytes) return 1;

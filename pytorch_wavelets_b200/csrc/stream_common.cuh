@@ -94,16 +94,18 @@ __device__ __forceinline__ void bulk_copy_g2s(float* smem_dst, const float* gsrc
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so a long
+  // hint keeps waiting warps out of the issue slots instead of spinning
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680)
       : "memory");
 }
 
