@@ -264,18 +264,53 @@ static void dwt_ws_layout(int planes, int H, int W, int J, int Lw, int Lh, int m
   }
 }
 
+// How the levels of one DWTForward call are executed (one policy, decided from the arguments alone):
+//   kPyramidAll   all J levels in the fused pyramid kernel (one launch, no inter-level low-pass in device memory)
+//   kPyramidFirst level 1 in the pyramid kernel (TMA loads, bulk stores, writes the padded low-pass into the
+//                 workspace), deeper levels one streaming kernel each
+//   kLevels       one K1 launch per level
+// Measured on B200 (profiles/r02_notes.md): the pyramid kernel is register / shared-memory bound to 2 CTAs per SM
+// when it carries more than one level, which costs more than the hand-off traffic it saves on large planes, while
+// its single-level form (4 CTAs per SM) beats the streaming kernel; small planes favour the single launch.
+enum DwtPolicy { kLevels = 0, kPyramidFirst = 1, kPyramidAll = 2 };
+
+#ifndef B200W_PYR_FUSE_ALL_MAX_SIDE
+#define B200W_PYR_FUSE_ALL_MAX_SIDE 0   /* planes up to this side use kPyramidAll (0: never, set from measurements) */
+#endif
+
+static DwtPolicy dwt_policy(PyrParams& pp, const float* x, long long xps, int xpitch, int planes, int H, int W, int J,
+                            int Lw, int Lh, int mode, bool generic) {
+  if (generic || Lw != Lh) return kLevels;
+  const bool small = (H <= B200W_PYR_FUSE_ALL_MAX_SIDE && W <= B200W_PYR_FUSE_ALL_MAX_SIDE);
+  if ((J == 1 || small) && fast::plan_dwt_pyramid(pp, x, xps, xpitch, planes, H, W, J, Lw, mode, 0) == 0)
+    return kPyramidAll;
+  if (J >= 2) {
+    const int wo = coeff_len(W, Lw, mode);
+    if (wo > 0 && fast::plan_dwt_pyramid(pp, x, xps, xpitch, planes, H, W, 1, Lw, mode, (wo + 31) / 32 * 32) == 0)
+      return kPyramidFirst;
+  }
+  return kLevels;
+}
+
 long long b200w_dwt_forward_workspace(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W,
                                       int J, int Lw, int Lh, int mode) {
   if (!dwt_mode_ok(mode)) return B200W_EMODE;
   if (planes < 0 || H < 1 || W < 1 || J < 1) return B200W_ESIZE;
   if (Lw < 2 || Lh < 2 || Lw > kMaxTaps || Lh > kMaxTaps) return B200W_EFILTER;
-  if (Lw == Lh) {
-    PyrParams pp;
-    if (fast::plan_dwt_pyramid(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, mode) == 0) return 0;
-  }
+  PyrParams pp;
+  if (dwt_policy(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, Lh, mode, false) == kPyramidAll) return 0;
   long long b[2];
   dwt_ws_layout(planes, H, W, J, Lw, Lh, mode, b);
   return b[0] + b[1];
+}
+
+static void pyr_set_taps(PyrParams& pp, const float* fw_lo, const float* fw_hi, const float* fh_lo, const float* fh_hi,
+                         int L) {
+  for (int i = 0; i < kPyrMaxTaps; ++i) {
+    const bool on = i < L;
+    pp.fw[2 * i] = on ? fw_lo[i] : 0.f; pp.fw[2 * i + 1] = on ? fw_hi[i] : 0.f;
+    pp.fh_lo[i] = on ? fh_lo[i] : 0.f; pp.fh_hi[i] = on ? fh_hi[i] : 0.f;
+  }
 }
 
 static int dwt_forward_impl(const float* x, long long x_plane_stride, int x_pitch, int planes, int H, int W, int J,
@@ -283,26 +318,20 @@ static int dwt_forward_impl(const float* x, long long x_plane_stride, int x_pitc
                             const float* fh_lo, const float* fh_hi, int Lh, int mode, void* workspace,
                             long long workspace_bytes, void* stream, bool generic) {
   if (!dwt_mode_ok(mode)) return B200W_EMODE;
-  if (!x || !yl || !highs) return B200W_EARG;
+  if (!x || !yl || !highs || !fw_lo || !fw_hi || !fh_lo || !fh_hi) return B200W_EARG;
   if (planes < 0 || H < 1 || W < 1 || J < 1) return B200W_ESIZE;
   if (Lw < 2 || Lh < 2) return B200W_EFILTER;
   for (int j = 0; j < J; ++j)
     if (!highs[j]) return B200W_EARG;
-  if (!generic && Lw == Lh) {
-    PyrParams pp;
-    if (fast::plan_dwt_pyramid(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, mode) == 0) {
-      int rc;
-      if (!fw_lo || !fw_hi || !fh_lo || !fh_hi) return B200W_EARG;
-      for (int i = 0; i < kPyrMaxTaps; ++i) {
-        const bool on = i < Lw;
-        pp.fw[2 * i] = on ? fw_lo[i] : 0.f; pp.fw[2 * i + 1] = on ? fw_hi[i] : 0.f;
-        pp.fh_lo[i] = on ? fh_lo[i] : 0.f; pp.fh_hi[i] = on ? fh_hi[i] : 0.f;
-      }
-      pp.yl = yl;
-      for (int j = 0; j < kPyrMaxLevels; ++j) pp.highs[j] = (j < J) ? highs[j] : nullptr;
-      rc = fast::launch_dwt_pyramid(pp, (cudaStream_t)stream);
-      if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
-    }
+  PyrParams pp;
+  DwtPolicy pol = dwt_policy(pp, x, x_plane_stride, x_pitch, planes, H, W, J, Lw, Lh, mode, generic);
+  if (pol == kPyramidAll) {
+    pyr_set_taps(pp, fw_lo, fw_hi, fh_lo, fh_hi, Lw);
+    pp.yl = yl;
+    for (int j = 0; j < kPyrMaxLevels; ++j) pp.highs[j] = (j < J) ? highs[j] : nullptr;
+    const int rc = fast::launch_dwt_pyramid(pp, (cudaStream_t)stream);
+    if (rc != fast::kNoFastPath) return rc ? rc : check_launch();
+    pol = kLevels;
   }
   long long wb[2];
   dwt_ws_layout(planes, H, W, J, Lw, Lh, mode, wb);
@@ -317,8 +346,17 @@ static int dwt_forward_impl(const float* x, long long x_plane_stride, int x_pitc
     const bool last = (j == J - 1);
     const int wp = last ? wo : (wo + 31) / 32 * 32;
     float* ll = last ? yl : buf[j & 1];
-    const int rc = dwt_afb2d_impl(src, sps, spitch, ll, (long long)ho * wp, wp, highs[j], planes, h, w, fw_lo, fw_hi,
-                                  Lw, fh_lo, fh_hi, Lh, mode, stream, generic);
+    int rc = fast::kNoFastPath;
+    if (j == 0 && pol == kPyramidFirst) {   // (J >= 2, so ll is the padded workspace buffer the plan was made for)
+      pyr_set_taps(pp, fw_lo, fw_hi, fh_lo, fh_hi, Lw);
+      pp.yl = ll;
+      for (int i = 0; i < kPyrMaxLevels; ++i) pp.highs[i] = (i == 0) ? highs[0] : nullptr;
+      rc = fast::launch_dwt_pyramid(pp, (cudaStream_t)stream);
+      if (rc == 0) rc = check_launch();
+    }
+    if (rc == fast::kNoFastPath)
+      rc = dwt_afb2d_impl(src, sps, spitch, ll, (long long)ho * wp, wp, highs[j], planes, h, w, fw_lo, fw_hi, Lw, fh_lo,
+                          fh_hi, Lh, mode, stream, generic);
     if (rc) return rc;
     src = ll; sps = (long long)ho * wp; spitch = wp; h = ho; w = wo;
   }

@@ -32,6 +32,8 @@ __device__ unsigned long long g_pyr_prof[64];   // [role (0 producer, 1 writer, 
 #define PYR_FLUSH(role, lane) do {} while (0)
 #endif
 
+constexpr int kPyrSplitC = 1, kPyrNSlotC = 4;   // the shape the kernel is compiled for (plan_pyramid_best only offers it)
+
 template <int L>
 struct PyrCfg {
   static constexpr int NC = kPyrNC;
@@ -59,6 +61,11 @@ __device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
+// wait used by the lightly loaded roles (producer, levels >= 1): poll + sleep instead of the hardware try_wait loop, whose
+// wake-ups (any barrier traffic on the SM) make the idle warps spin through the issue slots the level-1 warps need
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {
+  while (!mbar_test(bar, parity)) __nanosleep(200);
+}
 __device__ __forceinline__ void bulk_store_s2g(float* gdst, unsigned ssrc, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
@@ -82,7 +89,7 @@ __device__ __forceinline__ int pyr_phase(const float* band_base) {
 __device__ __forceinline__ float* pyr_band_base(const PyrParams& p, int l, int b, int plane) {
   const PyrLevel& v = p.lv[l];
   const long long band = (long long)v.Ho * v.Wo;
-  if (b == 3) return p.yl + (long long)plane * band;
+  if (b == 3) return p.yl + (long long)plane * v.Ho * p.ll_pitch;
   return p.highs[l] + ((long long)plane * 3 + b) * band;
 }
 
@@ -101,8 +108,8 @@ __device__ __forceinline__ void pyr_producer(const PyrParams& p, int plane, floa
   PYR_DECL();
 #pragma unroll 1
   for (int q = 0; q < n_slots; ++q) {
-    const int slot = q % kPyrNSlot;
-    const int use = q / kPyrNSlot;
+    const int slot = q % kPyrNSlotC;
+    const int use = q / kPyrNSlotC;
     if (use > 0) { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_in + v.n_in + slot), (unsigned)((use - 1) & 1)); PYR_ACC(0); }
     // row j of the slot holds extended row e = q*HS + j - PL
     int src = -1;
@@ -132,13 +139,29 @@ __device__ __forceinline__ void pyr_producer(const PyrParams& p, int plane, floa
 template <int L>
 __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float* smem, unsigned bar0, int lane) {
   using C = PyrCfg<L>;
-  int next_g[kPyrMaxLevels];
-#pragma unroll
-  for (int l = 0; l < kPyrMaxLevels; ++l) next_g[l] = 0;
-  int prev_l = -1, prev_g = 0;      // last event whose bulk reads are not yet known to be complete
+  const int SG = C::HS / kPyrSplitC;             // rows per staging group
+  const int R = kPyrNGO * SG;                    // rows in a staging ring
+  // lanes 0..3: the 16-byte aligned middle of one band each; lanes 8..31: one head / tail element of a band each
+  const bool bulk_lane = lane < 4;
+  const int myb = bulk_lane ? lane : (lane >= 8 ? (lane - 8) / 6 : 4);
+  const int mye = (lane >= 8) ? (lane - 8) % 6 : 0;
+  float* gb[kPyrMaxLevels];      // this lane's band in global memory, per level
+  unsigned stb[kPyrMaxLevels];   // ... and its staging ring
+  int ph[kPyrMaxLevels], next_g[kPyrMaxLevels], rslot[kPyrMaxLevels];
   int remaining = 0;
-  for (int l = 0; l < p.J; ++l) remaining += p.lv[l].n_stage;
-  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+#pragma unroll
+  for (int l = 0; l < kPyrMaxLevels; ++l) {
+    next_g[l] = 0; rslot[l] = 0; gb[l] = nullptr; stb[l] = 0; ph[l] = 0;
+    if (l < p.J) {
+      remaining += p.lv[l].n_stage * kPyrSplitC;
+      if (myb < p.lv[l].nbands) {
+        gb[l] = pyr_band_base(p, l, myb, plane);
+        ph[l] = pyr_phase(gb[l]);
+        stb[l] = (unsigned)__cvta_generic_to_shared(smem) + 4u * (unsigned)(p.lv[l].st_off + myb * p.lv[l].st_cap);   // band 3 follows three st_cap bands
+      }
+    }
+  }
+  int prev_bar = -1;      // out_empty barrier of the last event whose bulk reads are not yet known to be complete
   PYR_DECL();
 
   while (remaining > 0) {
@@ -148,44 +171,48 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
       if (l >= p.J) break;
       const PyrLevel& v = p.lv[l];
       const int g = next_g[l];
-      if (g >= v.n_stage) continue;
-      if (!__all_sync(0xffffffffu, mbar_test(bar0 + 8 * (v.bar_out + g % kPyrNGO), (unsigned)((g / kPyrNGO) & 1)))) continue;
+      if (g >= v.n_stage * kPyrSplitC) continue;
+      const int bar = v.bar_out + g % kPyrNGO;
+      if (!__all_sync(0xffffffffu, mbar_test(bar0 + 8 * bar, (unsigned)((g / kPyrNGO) & 1)))) continue;
       any = true;
       PYR_T0();
-      // rows [k0, k1) of the level = stream positions [s0, s1) of every band
-      const int k0 = imax(0, g * C::HS - C::PRO), k1 = imin(v.Ho, (g + 1) * C::HS - C::PRO);
-      const int s0 = k0 * v.Wo, s1 = k1 * v.Wo;
-      // lanes 0..3: the 16-byte aligned middle of one band each; lanes 8..31: head / tail elements
-      const int b = (lane < 4) ? lane : (lane - 8) / 6;
-      if (lane != 4 && lane != 5 && lane != 6 && lane != 7 && b < v.nbands) {
-        float* gb = pyr_band_base(p, l, b, plane);
-        const int a = pyr_phase(gb);
+      // rows [k0, k1) of the level = stream positions [s0, s1) of every band; the group starts at ring row rslot
+      const int k0 = imax(0, g * SG - C::PRO), k1 = imin(v.Ho, (g + 1) * SG - C::PRO);
+      if (k1 > k0 && gb[l] != nullptr) {
+        const int rowlen = (myb == 3) ? p.ll_pitch : v.Wo;     // the low-pass rows carry their pitch
+        const int cap = (myb == 3) ? v.st_cap_ll : v.st_cap;
+        const int s0 = k0 * rowlen, s1 = k1 * rowlen, a = ph[l];
         const int hd = imin(s1 - s0, (4 - ((s0 + a) & 3)) & 3);
         const int m0 = s0 + hd;
         const int m1 = m0 + ((s1 - m0) & ~3);
-        const unsigned st_s = smem_s + 4u * (unsigned)(v.st_off + b * v.st_cap);
-        if (lane < 4) {
+        int i0 = rslot[l] * rowlen + a;               // ring index of position s0 (may exceed the ring by < 4)
+        if (bulk_lane) {
           const int n = m1 - m0;
           if (n > 0) {
-            const int i0 = (m0 + a) % v.st_cap;
-            const int first = imin(n, v.st_cap - i0);
-            bulk_store_s2g(gb + m0, st_s + 4u * (unsigned)i0, 4u * (unsigned)first);
-            if (n > first) bulk_store_s2g(gb + m0 + first, st_s, 4u * (unsigned)(n - first));
+            int i = i0 + hd;
+            if (i >= cap) i -= cap;
+            const int first = imin(n, cap - i);
+            bulk_store_s2g(gb[l] + m0, stb[l] + 4u * (unsigned)i, 4u * (unsigned)first);
+            if (n > first) bulk_store_s2g(gb[l] + m0 + first, stb[l], 4u * (unsigned)(n - first));
           }
         } else {
-          const int e = (lane - 8) % 6;
           int pos = -1;
-          if (e < 3) { if (e < hd) pos = s0 + e; }
-          else if (e - 3 < s1 - m1) pos = m1 + (e - 3);
-          if (pos >= 0) gb[pos] = lds_s(st_s + 4u * (unsigned)((pos + a) % v.st_cap));
+          if (mye < 3) { if (mye < hd) pos = s0 + mye; }
+          else if (mye - 3 < s1 - m1) pos = m1 + (mye - 3);
+          if (pos >= 0) {
+            int i = i0 + (pos - s0);
+            while (i >= cap) i -= cap;
+            gb[l][pos] = lds_s(stb[l] + 4u * (unsigned)i);
+          }
         }
       }
+      if (k1 > k0) { rslot[l] += k1 - k0; if (rslot[l] >= R) rslot[l] -= R; }
       bulk_commit();
       // everything but this event's own bulk group has been read out of shared memory: release the previous event
       bulk_wait_read<1>();
       __syncwarp();
-      if (prev_l >= 0 && lane == 0) mbar_arrive(bar0 + 8 * (p.lv[prev_l].bar_out + kPyrNGO + prev_g % kPyrNGO));
-      prev_l = l; prev_g = g;
+      if (prev_bar >= 0 && lane == 0) mbar_arrive(bar0 + 8 * prev_bar);
+      prev_bar = bar + kPyrNGO;
       next_g[l] = g + 1;
       --remaining;
       PYR_ACC(0);   // time spent flushing events
@@ -194,15 +221,15 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
 #endif
     }
     if (!any) {
-      if (prev_l >= 0) {
+      if (prev_bar >= 0) {
         PYR_T0();
         bulk_wait_read<0>();
         PYR_ACC(2);
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8 * (p.lv[prev_l].bar_out + kPyrNGO + prev_g % kPyrNGO));
-        prev_l = -1;
+        if (lane == 0) mbar_arrive(bar0 + 8 * prev_bar);
+        prev_bar = -1;
       } else {
-        __nanosleep(64);
+        __nanosleep(100);
       }
     }
   }
@@ -264,7 +291,8 @@ template <int L>
 struct PyrEmit {
   unsigned st_s[4];     // staging band bases (shared-window byte addresses)
   unsigned so[4];       // byte offset of (current row slot, c0) inside the band's ring, phase included
-  unsigned capb, wob;   // ring size and row advance in bytes
+  unsigned capb, wob;   // ring size and row advance in bytes (band-pass bands)
+  unsigned capb3, wob3; // ... of the low-pass band of the last level (rows of ll_pitch floats)
   int nv, nb, kslot, R;
   unsigned nr_s;        // next level's ring: byte address of (row 0, column c0); 0 for the last level
   unsigned nr_off, nr_pitch4, nr_bytes;   // byte offset of the current row, row pitch, ring size
@@ -279,8 +307,9 @@ struct PyrEmit {
     } else {
 #pragma unroll
       for (int i = 0; i < kPyrNC; ++i) {
+        const unsigned cb = (b == 3) ? capb3 : capb;
         unsigned oi = so[b] + 4u * i;
-        if (oi >= capb) oi -= capb;
+        if (oi >= cb) oi -= cb;
         if (nv > i) sts_s(st_s[b] + oi, v[i]);
       }
     }
@@ -295,9 +324,10 @@ struct PyrEmit {
     putn(1, v1, wrap_slot);
     putn(2, v2, wrap_slot);
     if (nb == 4) putn(3, v3, wrap_slot);
-    const unsigned back = wrap_slot ? capb : 0u;   // the slot after the last one is slot 0
+    // the slot after the last one is slot 0
 #pragma unroll
-    for (int b = 0; b < 4; ++b) so[b] = so[b] + wob - back;
+    for (int b = 0; b < 3; ++b) so[b] = so[b] + wob - (wrap_slot ? capb : 0u);
+    so[3] = so[3] + wob3 - (wrap_slot ? capb3 : 0u);
     kslot = wrap_slot ? 0 : kslot + 1;
     if (nr_s != 0) {
       const unsigned rb = nr_s + nr_off;
@@ -329,7 +359,8 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
 
   PyrEmit<L> em;
   em.capb = 4u * (unsigned)v.st_cap; em.wob = 4u * (unsigned)v.Wo; em.nv = nv; em.nb = v.nbands;
-  em.kslot = 0; em.R = kPyrNGO * C::HS;
+  em.capb3 = 4u * (unsigned)v.st_cap_ll; em.wob3 = 4u * (unsigned)p.ll_pitch;
+  em.kslot = 0; em.R = kPyrNGO * (C::HS / kPyrSplitC);
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     em.st_s[b] = smem_s + 4u * (unsigned)(v.st_off + (b < v.nbands ? b : 0) * v.st_cap);
@@ -391,6 +422,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
   int g_seen = 0, g_rel = 0;   // levels >= 1: input groups waited for / released so far
   const int prev_stages = (lvl > 0) ? p.lv[lvl - 1].n_stage : 0;
   const int pitch4 = 4 * v.in_pitch;
+  constexpr int split = kPyrSplitC, nslot = kPyrNSlotC;
 
 #pragma unroll 1
   for (int t = 0; t < v.n_stage; ++t) {
@@ -398,7 +430,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
     if (lane < C::RS) {
       unsigned a;
       if (lvl == 0) {
-        const int slot = (2 * t + (lane >= C::HS ? 1 : 0)) % kPyrNSlot;
+        const int slot = (2 * t + (lane >= C::HS ? 1 : 0)) % nslot;
         a = ring_s + (unsigned)((slot * C::HS + (lane >= C::HS ? lane - C::HS : lane)) * pitch4);
       } else {
         const int e = t * C::RS + lane - C::PL;
@@ -407,8 +439,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
       }
       stsu_s(tab_s + 4u * lane, a);
     }
-    // ---- room for this stage's output group ---------------------------------------------------------------
-    if (t >= kPyrNGO) { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_out + kPyrNGO + t % kPyrNGO), (unsigned)((t / kPyrNGO - 1) & 1)); PYR_ACC(1); }
+    // ---- room for this stage's rows in the next level's ring (the staging groups are claimed inside the stage) ---
     if (!last && t >= nx_n) { PYR_T0(); mbar_wait(bar0 + 8 * (nx_bar + nx_n + t % nx_n), (unsigned)((t / nx_n - 1) & 1)); PYR_ACC(2); }
     // ---- inputs ----------------------------------------------------------------------------------------------
     if (lvl > 0) {
@@ -416,7 +447,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
                               prev_stages - 1);
       PYR_T0();
       while (g_seen <= g_need) {
-        mbar_wait(bar0 + 8 * (v.bar_in + g_seen % v.n_in), (unsigned)((g_seen / v.n_in) & 1));
+        mbar_wait_relaxed(bar0 + 8 * (v.bar_in + g_seen % v.n_in), (unsigned)((g_seen / v.n_in) & 1));
         ++g_seen;
       }
       PYR_ACC(0);
@@ -425,14 +456,22 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
     const int k_first = t * C::HS - C::PRO;
 #pragma unroll
     for (int hh = 0; hh < C::HS; ++hh) {
+      if (hh == 0 || (split == 2 && hh == C::HS / 2)) {   // a new staging group: its ring rows must have been flushed
+        const int sg = t * split + (hh ? 1 : 0);
+        if (sg >= kPyrNGO) {
+          PYR_T0();
+          mbar_wait(bar0 + 8 * (v.bar_out + kPyrNGO + sg % kPyrNGO), (unsigned)((sg / kPyrNGO - 1) & 1));
+          PYR_ACC(1);
+        }
+      }
       if (lvl == 0 && (hh == 0 || hh == C::HS / 2)) {
         const int q = 2 * t + (hh ? 1 : 0);
         if (hh) {   // done with the first slot of the stage
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (q - 1) % kPyrNSlot));
+          if (lane == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (q - 1) % nslot));
         }
-        const int slot = q % kPyrNSlot;
-        { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_in + slot), (unsigned)((q / kPyrNSlot) & 1)); PYR_ACC(0); }
+        const int slot = q % nslot;
+        { PYR_T0(); mbar_wait(bar0 + 8 * (v.bar_in + slot), (unsigned)((q / nslot) & 1)); PYR_ACC(0); }
         if (do_patch) {
           PYR_T0();
           if (patch_dst >= 0) {
@@ -465,6 +504,11 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
         em.row(lo, hi);
         PYR_ACC(5);
       }
+      if (split == 2 && hh == C::HS / 2 - 1) {   // a staging group ends inside the stage: publish it
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (v.bar_out + (t * split) % kPyrNGO));
+      }
     }
     // ---- hand the inputs back, publish the outputs -----------------------------------------------------------
 #ifdef B200W_PYR_PROF
@@ -476,8 +520,8 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
     prof[3] += (unsigned long long)(clock64() - pyr_tf_);
 #endif
     if (lane == 0) {
-      if (lvl == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (2 * t + 1) % kPyrNSlot));
-      mbar_arrive(bar0 + 8 * (v.bar_out + t % kPyrNGO));
+      if (lvl == 0) mbar_arrive(bar0 + 8 * (v.bar_in + v.n_in + (2 * t + 1) % nslot));
+      mbar_arrive(bar0 + 8 * (v.bar_out + (t * split + split - 1) % kPyrNGO));
       if (!last) mbar_arrive(bar0 + 8 * (nx_bar + t % nx_n));
     }
     if (lvl > 0) {
@@ -539,24 +583,30 @@ __global__ void __launch_bounds__(MAXT, MINB) dwt_pyramid(const __grid_constant_
   }
 }
 
-constexpr int kPyrSmallThreads = (kPyrNC >= 3) ? 256 : 384;   // largest CTA that still runs two per SM
-
-template <int L>
-inline int launch_pyramid(const PyrParams& p, cudaStream_t stream) {
-  if (p.planes <= 0) return 0;
+template <int L, int MAXT, int MINB>
+inline int launch_pyramid_v(const PyrParams& p, cudaStream_t stream, int slot) {
   static int smem_set[64] = {};
   int dev = 0;
   (void)cudaGetDevice(&dev);
-  const bool small = p.threads <= kPyrSmallThreads;
-  if (dev < 0 || dev >= 64 || !(smem_set[dev] & (small ? 1 : 2))) {
-    cudaError_t e = small ? cudaFuncSetAttribute(dwt_pyramid<L, kPyrSmallThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                          : cudaFuncSetAttribute(dwt_pyramid<L, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return kNoFastPath; }
-    if (dev >= 0 && dev < 64) smem_set[dev] |= (small ? 1 : 2);
+  (void)slot;
+  if (dev < 0 || dev >= 64 || !smem_set[dev]) {
+    if (cudaFuncSetAttribute(dwt_pyramid<L, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return kNoFastPath;
+    }
+    if (dev >= 0 && dev < 64) smem_set[dev] = 1;
   }
-  if (small) dwt_pyramid<L, kPyrSmallThreads, 2><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
-  else dwt_pyramid<L, 512, 1><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
+  dwt_pyramid<L, MAXT, MINB><<<(unsigned)p.planes, p.threads, p.smem_bytes, stream>>>(p);
   return 0;
+}
+
+// three instantiations by CTA size (pyr_ctas_for_threads in pyramid_plan.h mirrors the MINB values)
+template <int L>
+inline int launch_pyramid(const PyrParams& p, cudaStream_t stream) {
+  if (p.planes <= 0) return 0;
+  if (p.threads <= 160) return launch_pyramid_v<L, 160, B200W_PYR_MINB_SMALL>(p, stream, 0);
+  if (p.threads <= 256) return launch_pyramid_v<L, 256, 2>(p, stream, 1);
+  return launch_pyramid_v<L, 512, 1>(p, stream, 2);
 }
 
 }  // namespace fast

@@ -23,8 +23,9 @@ int try_launch_inv_j2plus(const DtParams& p, cudaStream_t stream);
 
 // fused multi-level DWT analysis (k_pyramid.cu): plan_dwt_pyramid fills everything but the output pointers and the
 // taps and returns kNoFastPath when the fused kernel does not apply (then run the levels one by one)
+// (ll_pitch: row pitch of the final low-pass the kernel writes, 0 = contiguous)
 int plan_dwt_pyramid(PyrParams& p, const float* x, long long xps, int xpitch, int planes, int H, int W, int J, int L,
-                     int mode);
+                     int mode, int ll_pitch);
 int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream);
 
 }  // namespace fast

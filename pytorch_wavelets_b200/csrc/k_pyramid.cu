@@ -19,9 +19,25 @@ static int max_optin_smem() {
   return cache[dev];
 }
 
+static int sm_smem() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 228 * 1024;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess || v <= 0) {
+      (void)cudaGetLastError();
+      v = 228 * 1024;
+    }
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
 int plan_dwt_pyramid(PyrParams& p, const float* x, long long xps, int xpitch, int planes, int H, int W, int J, int L,
-                     int mode) {
-  return plan_pyramid(p, planes, H, W, J, L, mode, xps, xpitch, x, max_optin_smem()) ? kNoFastPath : 0;
+                     int mode, int ll_pitch) {
+  return plan_pyramid_best(p, planes, H, W, J, L, mode, xps, xpitch, x, max_optin_smem(), sm_smem(), ll_pitch)
+             ? kNoFastPath : 0;
 }
 
 int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream) {

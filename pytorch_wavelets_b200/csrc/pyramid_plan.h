@@ -27,8 +27,7 @@ constexpr int kPyrMaxTaps = 16;
 #define B200W_PYR_NC 3
 #endif
 constexpr int kPyrNC = B200W_PYR_NC;      // output columns per lane
-constexpr int kPyrNGO = 2;     // staging groups per level
-constexpr int kPyrNSlot = 4;   // input-ring slots (half a level-1 stage each)
+constexpr int kPyrNGO = 2;     // staging groups per level (ring depth)
 constexpr int kPyrAuxWarps = 2;  // warp 0 = producer, warp 1 = writer
 
 struct PyrLevel {
@@ -38,7 +37,8 @@ struct PyrLevel {
   int in_off, in_pitch, in_rows;  // input ring: float offset in dynamic smem, row pitch (floats), depth (rows)
   int n_in;                     // barriers per direction on the input ring: slots (level 0) / groups (levels >= 1)
   int bar_in;                   // index of in_full[0]; in_empty[0] = bar_in + n_in
-  int st_off, st_cap, nbands;   // staging: float offset of band 0, floats per band (multiple of 32), 3 (+1: final ll)
+  int st_off, st_cap, nbands;   // staging: float offset of band 0, floats per band (multiple of 4), 3 (+1: final ll)
+  int st_cap_ll;                // last level: floats of the low-pass band's ring (rows of ll_pitch floats)
   int bar_out;                  // index of out_full[0]; out_empty[0] = bar_out + kPyrNGO
 };
 
@@ -47,6 +47,9 @@ struct PyrParams {
   float* yl;
   float* highs[kPyrMaxLevels];
   int planes, J, mode, L;
+  int nslot;                    // input-ring slots (half a level-1 stage each): 3 or 4
+  int split;                    // staging groups per worker stage (a group = HS / split output rows): 1 or 2
+  int ll_pitch;                 // row pitch (floats) of the final low-pass in global memory (>= its width)
   int zero_off;                 // a row of zeros (floats) for zero-padding rows of levels >= 1
   int tab_off;                  // per-warp tables of the current stage's row addresses (32 words per warp)
   int n_bars, smem_bytes, threads;
@@ -89,8 +92,10 @@ B200W_HD int pyr_stage_release_bound(int t, int RS, int PL, int H, int L) {
 
 // ---- the plan -----------------------------------------------------------------------------------------------
 // Returns 0 and fills p (everything except pointers and taps), or 1 when the fused kernel does not apply.
+// nslot / split / extra_in: shared-memory shape (see plan_pyramid_best); ll_pitch: row pitch of the final low-pass (0 = its width)
 inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, int mode, long long xps, int xpitch,
-                        const void* x, int max_smem_bytes) {
+                        const void* x, int max_smem_bytes, int nslot = 4, int split = 1, int extra_in = 1,
+                        int ll_pitch = 0) {
   if (J < 1 || J > kPyrMaxLevels) return 1;
   if (L < 2 || (L & 1) || L > 16) return 1;
   if (mode != B200W_MODE_ZERO && mode != B200W_MODE_SYMMETRIC && mode != B200W_MODE_REFLECT) return 1;
@@ -98,6 +103,8 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
   if ((W & 3) || (xpitch & 3) || (xps & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
   const int HS = pyr_hs(L), RS = 2 * HS, PL = L - 2, PRO = PL / 2, HALO = pyr_halo(L);
   p.planes = planes; p.J = J; p.mode = mode; p.L = L;
+  p.nslot = nslot; p.split = split;
+  if (nslot < 3 || nslot > 4 || (split != 1 && split != 2) || (HS % split)) return 1;
   int warp = kPyrAuxWarps;
   int h = H, w = W;
   int nbar = 0;
@@ -117,8 +124,8 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
     v.in_pitch = (HALO + 2 * (v.Wo + kPyrNC - 2) + 2 + 3) / 4 * 4;
     if (v.in_pitch < HALO + w + L - 1) v.in_pitch = (HALO + w + L - 1 + 3) / 4 * 4;
     if (l == 0) {
-      v.n_in = kPyrNSlot;
-      v.in_rows = kPyrNSlot * HS;
+      v.n_in = nslot;
+      v.in_rows = nslot * HS;
     } else {
       // groups of the previous level that must be resident at once: simulate the consumer's stage sequence
       const PyrLevel& u = p.lv[l - 1];
@@ -129,15 +136,21 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
         const int lo = pyr_stage_release_bound(t, RS, PL, h, L);
         while (rel < u.n_stage && pyr_group_end(rel, HS, PRO) <= lo) ++rel;
       }
-      v.n_in = need + 1;                         // one more so the producing level can work ahead
+      v.n_in = need + extra_in;                  // (+1: the producing level can work a group ahead)
       v.in_rows = v.n_in * HS;
     }
     v.in_off = off; off += v.in_rows * v.in_pitch;
     v.bar_in = nbar; nbar += 2 * v.n_in;
     v.nbands = (l == J - 1) ? 4 : 3;
-    v.st_cap = kPyrNGO * HS * v.Wo;              // whole rows (a multiple of 4 floats: kPyrNGO * HS % 4 == 0)
-    v.st_off = off; off += v.nbands * v.st_cap;
-    off = (off + 3) / 4 * 4;
+    v.st_cap = kPyrNGO * (HS / split) * v.Wo;    // whole rows
+    v.st_cap_ll = 0;
+    if (l == J - 1) {
+      p.ll_pitch = (ll_pitch > 0) ? ll_pitch : v.Wo;
+      if (p.ll_pitch < v.Wo) return 1;
+      v.st_cap_ll = kPyrNGO * (HS / split) * p.ll_pitch;
+    }
+    if ((v.st_cap & 3) || (v.st_cap_ll & 3)) return 1;   // the rings must wrap on a 16-byte boundary
+    v.st_off = off; off += 3 * v.st_cap + v.st_cap_ll;
     v.bar_out = nbar; nbar += 2 * kPyrNGO;
     h = v.Ho; w = v.Wo;
   }
@@ -154,6 +167,40 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
   p.threads = 32 * warp;
   if (p.threads > 512 || p.smem_bytes > max_smem_bytes) return 1;
   p.x = static_cast<const float*>(x); p.xps = xps; p.xpitch = xpitch;
+  return 0;
+}
+
+// CTAs per SM the kernel instantiation for `threads` is compiled for (__launch_bounds__ in dwt_pyramid.cuh)
+#ifndef B200W_PYR_MINB_SMALL
+#define B200W_PYR_MINB_SMALL 3
+#endif
+inline int pyr_ctas_for_threads(int threads) { return threads <= 160 ? B200W_PYR_MINB_SMALL : (threads <= 256 ? 2 : 1); }
+
+// Picks the shared-memory shape that lets the most CTAs share an SM (up to what the register budget of the matching
+// kernel instantiation allows), preferring the deeper rings among equals.
+inline int plan_pyramid_best(PyrParams& p, int planes, int H, int W, int J, int L, int mode, long long xps, int xpitch,
+                             const void* x, int max_smem_bytes, int sm_smem_bytes, int ll_pitch = 0) {
+#ifdef B200W_PYR_FORCE_NSLOT   /* experiments: one fixed shape */
+#define B200W_PYR_FS {B200W_PYR_FORCE_NSLOT, B200W_PYR_FORCE_SPLIT, 1}
+  static const int shapes[4][3] = {B200W_PYR_FS, B200W_PYR_FS, B200W_PYR_FS, B200W_PYR_FS};
+#else
+  // (smaller shapes -- 3 input slots, half-stage staging groups, no spare ring group -- fit a third 8-warp CTA per SM,
+  // but the kernel then has to live in 80 registers and spills: measured 2.6x slower, profiles/r02_notes.md)
+  static const int shapes[4][3] = {{4, 1, 1}, {4, 1, 1}, {4, 1, 1}, {4, 1, 1}};
+#endif
+  PyrParams best;
+  int best_ctas = 0;
+  for (int i = 0; i < 4; ++i) {
+    PyrParams q;
+    if (plan_pyramid(q, planes, H, W, J, L, mode, xps, xpitch, x, max_smem_bytes, shapes[i][0], shapes[i][1],
+                     shapes[i][2], ll_pitch))
+      continue;
+    const int by_smem = sm_smem_bytes / (q.smem_bytes + 1024);
+    const int ctas = imin(by_smem, pyr_ctas_for_threads(q.threads));
+    if (ctas > best_ctas) { best_ctas = ctas; best = q; }
+  }
+  if (best_ctas == 0) return 1;
+  p = best;
   return 0;
 }
 

@@ -109,12 +109,13 @@ int emu_dtcwt_inv_j2plus(const float* ll, long long llps, int llpitch, const flo
 // The shipped host-side plan of the fused pyramid kernel (pyramid_plan.h), flattened for the CPU tests:
 // out = {rc, smem_bytes, threads, n_bars, zero_off, then per level: H, W, Ho, Wo, n_stage, warp0, nwarps, in_off,
 //        in_pitch, in_rows, n_in, bar_in, st_off, st_cap, nbands, bar_out}
-int emu_plan_pyramid(int planes, int H, int W, int J, int L, int mode, int xpitch, int max_smem, int* out) {
+int emu_plan_pyramid(int planes, int H, int W, int J, int L, int mode, int xpitch, int max_smem, int ll_pitch, int* out) {
   PyrParams p;
   memset(&p, 0, sizeof(p));
   alignas(16) static float dummy[4];
-  const int rc = plan_pyramid(p, planes, H, W, J, L, mode, (long long)H * xpitch, xpitch, dummy, max_smem);
+  const int rc = plan_pyramid_best(p, planes, H, W, J, L, mode, (long long)H * xpitch, xpitch, dummy, max_smem, 228 * 1024, ll_pitch);
   out[0] = rc; out[1] = p.smem_bytes; out[2] = p.threads; out[3] = p.n_bars; out[4] = p.zero_off;
+  out[5 + 16 * 4] = p.nslot; out[6 + 16 * 4] = p.split; out[7 + 16 * 4] = p.ll_pitch;
   if (rc) return rc;
   for (int l = 0; l < J; ++l) {
     const PyrLevel& v = p.lv[l];

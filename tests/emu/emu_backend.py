@@ -164,13 +164,15 @@ PLAN_FIELDS = ('H', 'W', 'Ho', 'Wo', 'n_stage', 'warp0', 'nwarps', 'in_off', 'in
                'st_off', 'st_cap', 'nbands', 'bar_out')
 
 
-def plan_pyramid(planes, H, W, J, L, mode, xpitch=None, max_smem=227 * 1024):
+def plan_pyramid(planes, H, W, J, L, mode, xpitch=None, max_smem=227 * 1024, ll_pitch=0):
     """The shipped plan of the fused DWT pyramid kernel (pyramid_plan.h) as a dict, or None when it does not apply."""
-    out = (ctypes.c_int * (5 + 16 * 4))()
-    rc = lib().emu_plan_pyramid(planes, H, W, J, L, orc.mode_int(mode), W if xpitch is None else xpitch, max_smem, out)
+    out = (ctypes.c_int * (8 + 16 * 4))()
+    rc = lib().emu_plan_pyramid(planes, H, W, J, L, orc.mode_int(mode), W if xpitch is None else xpitch, max_smem,
+                                ll_pitch, out)
     if rc:
         return None
-    d = {'smem_bytes': out[1], 'threads': out[2], 'n_bars': out[3], 'zero_off': out[4], 'levels': []}
+    d = {'smem_bytes': out[1], 'threads': out[2], 'n_bars': out[3], 'zero_off': out[4], 'nslot': out[69],
+         'split': out[70], 'll_pitch': out[71], 'levels': []}
     for l in range(J):
         d['levels'].append(dict(zip(PLAN_FIELDS, out[5 + 16 * l: 5 + 16 * (l + 1)])))
     return d
