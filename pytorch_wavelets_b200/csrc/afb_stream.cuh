@@ -108,7 +108,7 @@ __device__ __forceinline__ void afb_stage(const AfbParams& p, const float* s0, f
     float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      const float2 f = make_float2(p.fw_lo.t[j], p.fw_hi.t[j]);
+      const float2 f = make_float2(p.fwp[2 * j], p.fwp[2 * j + 1]);
       ra = ffma2_s(xa[C::OFF + 2 * o + j], f, ra);
       rb = ffma2_s(xb[C::OFF + 2 * o + j], f, rb);
     }

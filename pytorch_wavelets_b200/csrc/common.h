@@ -45,7 +45,7 @@ constexpr float kInvSqrt2 = 0.70710678118654752440f;
 
 // Filter taps travel as kernel parameters (constant bank): with a compile-time tap index the FFMA
 // takes its coefficient straight from c[0x0][..]; with a runtime index it is one LDC.
-struct Taps {
+struct alignas(16) Taps {
   float t[kMaxTaps];
 };
 
@@ -100,6 +100,9 @@ struct AfbParams {  // K1
   int tiles_x, tiles_y;
   Taps fw_lo, fw_hi, fh_lo, fh_hi;
   int hipitch;        // experiments only (streaming kernel): row pitch of the band-pass planes, 0 = Wo
+  // the W-pass taps once more as interleaved {low-pass, high-pass} pairs: one aligned 64-bit constant load feeds a
+  // packed FMA (pairs built from two separate arrays cost two extra uniform moves per FFMA2)
+  alignas(16) float fwp[2 * kMaxTaps];
 };
 
 struct SfbParams {  // K2
@@ -123,6 +126,9 @@ struct DtParams {  // K3..K7
   float magbias, magbias2;
   int tiles_x, tiles_y;
   Taps f0, f1, f2, f3;                             // level 1: f0=h0/g0, f1=h1/g1; q-shift: f0=*0a f1=*1a f2=*0b f3=*1b
+  // q-shift forward: interleaved pairs {f2[j], f0[j]} (low-pass trees b, a) and {f3[j], f1[j]} (high-pass trees)
+  alignas(16) float qlo[2 * kMaxTaps];
+  alignas(16) float qhi[2 * kMaxTaps];
 };
 
 }  // namespace b200w

@@ -294,8 +294,8 @@ __device__ __forceinline__ void j2_stage(const DtParams& p, const float* s0, flo
 #pragma unroll
     for (int j = 0; j < MQ; ++j) {
       const float2 xv = make_float2(x[C::OFF + 2 * j], x[C::OFF + 2 * j + 1]);
-      l = ffma2(xv, make_float2(p.f2.t[j], p.f0.t[j]), l);  // {Ya with h0b, Yb with h0a}
-      h = ffma2(xv, make_float2(p.f3.t[j], p.f1.t[j]), h);  // {Ya with h1b, Yb with h1a}
+      l = ffma2(xv, make_float2(p.qlo[2 * j], p.qlo[2 * j + 1]), l);  // {Ya with h0b, Yb with h0a}
+      h = ffma2(xv, make_float2(p.qhi[2 * j], p.qhi[2 * j + 1]), h);  // {Ya with h1b, Yb with h1a}
     }
     const int S = (4 * U + r) % WR;
     wl[S] = l;

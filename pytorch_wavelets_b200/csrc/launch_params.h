@@ -48,6 +48,7 @@ inline int build_afb(AfbParams& p, const float* x, long long xps, int xpitch, fl
   if ((rc = set_taps(p.fw_lo, fw_lo, Lw)) || (rc = set_taps(p.fw_hi, fw_hi, Lw)) ||
       (rc = set_taps(p.fh_lo, fh_lo, Lh)) || (rc = set_taps(p.fh_hi, fh_hi, Lh)))
     return rc;
+  for (int i = 0; i < kMaxTaps; ++i) { p.fwp[2 * i] = p.fw_lo.t[i]; p.fwp[2 * i + 1] = p.fw_hi.t[i]; }
   p.x = x; p.xps = xps; p.xpitch = xpitch;
   p.ll = ll; p.llps = llps; p.llpitch = llpitch;
   p.hipitch = 0;
@@ -145,6 +146,10 @@ inline int build_fwd_j2plus(DtParams& p, const float* x, long long xps, int xpit
   if ((rc = set_taps(p.f0, h0a, m)) || (rc = set_taps(p.f1, h1a, m)) || (rc = set_taps(p.f2, h0b, m)) ||
       (rc = set_taps(p.f3, h1b, m)))
     return rc;
+  for (int i = 0; i < kMaxTaps; ++i) {
+    p.qlo[2 * i] = p.f2.t[i]; p.qlo[2 * i + 1] = p.f0.t[i];
+    p.qhi[2 * i] = p.f3.t[i]; p.qhi[2 * i + 1] = p.f1.t[i];
+  }
   if (xpitch < W || llpitch < W / 2) return B200W_EARG;
   p.in = x; p.inps = xps; p.inpitch = xpitch;
   p.out = ll; p.outps = llps; p.outpitch = llpitch;
