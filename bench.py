@@ -428,17 +428,22 @@ def run_ours(args):
     if world > 1 and not args.no_gather:
         try:
             gsteps = min(args.steps, 5)
+            try:     # the C ABI's own NCCL communicator; torch.distributed's NCCL group if it cannot be created
+                comm = parallel.Communicator.from_torch_distributed()
+                transport = 'b200w_allgather (C ABI, NCCL communicator created with b200w_comm_init)'
+            except Exception as exc:
+                comm, transport = None, 'torch.distributed.all_gather (NCCL); C-ABI communicator unavailable: %r' % (exc,)
             with torch.no_grad():
-                out = parallel.gather_pyramid(dwt(xd), world * dshape[0])
-                out2 = parallel.gather_pyramid(dtc(xt), world * tshape[0])
+                out = parallel.gather_pyramid(dwt(xd), world * dshape[0], comm=comm)
+                out2 = parallel.gather_pyramid(dtc(xt), world * tshape[0], comm=comm)
                 gbytes = sum(t.numel() * 4 for t in [out[0]] + list(out[1])) + sum(t.numel() * 4 for t in [out2[0]] + list(out2[1]))
                 del out, out2
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(gsteps):
-                    o1 = parallel.gather_pyramid(dwt(xd), world * dshape[0])
-                    o2 = parallel.gather_pyramid(dtc(xt), world * tshape[0])
+                    o1 = parallel.gather_pyramid(dwt(xd), world * dshape[0], comm=comm)
+                    o2 = parallel.gather_pyramid(dtc(xt), world * tshape[0], comm=comm)
                     del o1, o2
                 e1.record()
                 barrier()
@@ -449,6 +454,7 @@ def run_ours(args):
             recv = gbytes * (world - 1) / world
             gather = {'value_with_gather': world * (pix_d + pix_t) * gsteps / tg / 1e6, 'unit': 'Mpix/s',
                       'ms_per_step': 1e3 * tg / gsteps, 'collective': 'NCCL all_gather of yl and every yh[j], both transforms',
+                      'transport': transport,
                       'gathered_bytes_per_rank': gbytes, 'received_bytes_per_rank': recv,
                       'collective_ms': 1e3 * t_coll, 'recv_GBps_per_rank': recv / max(t_coll, 1e-9) / 1e9, 'steps': gsteps}
         except Exception as exc:

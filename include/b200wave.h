@@ -206,6 +206,25 @@ int b200w_scat_j1(const float* x, float* z, float* dre_dr, float* dim_dr,
                   int mode, float magbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU.  Every (n, c) plane is transformed independently (depthwise filters, no halo between planes:
+ * reference dwt/lowlevel.py:143,164,168; dtcwt/lowlevel.py:77,111), so the batch shards over the GPUs of a
+ * box with NO exchange during compute; the one collective of the path is the all-gather of the returned
+ * tensors along dim 0 after the last level.  One process per GPU; the communicator is an explicit handle
+ * (no hidden global state).  NCCL is bound at run time; without it these return B200W_ENOTIMPL.
+ *   b200w_comm_unique_id  rank 0 creates the 128-byte NCCL id and hands it to the other ranks out of band
+ *                         (the Python shell broadcasts it through torch.distributed)
+ *   b200w_comm_init       collective over all ranks; binds the communicator to the CURRENT CUDA device
+ *   b200w_allgather       recv[r*count .. (r+1)*count) = rank r's send[0 .. count)  (fp32 elements), asynchronous
+ *                         on `stream` (pass the compute stream: the gather then simply follows the last level)
+ */
+typedef struct b200w_comm b200w_comm;
+int b200w_comm_unique_id(void* id128);
+int b200w_comm_init(b200w_comm** comm, int rank, int world, const void* id128);
+int b200w_comm_destroy(b200w_comm* comm);
+int b200w_allgather(b200w_comm* comm, const float* send, float* recv, long long count, void* stream);
+const char* b200w_comm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
  * Generic-kernel variants.  Every entry point above picks a specialised streaming kernel when one
  * exists for the filter lengths / layout / alignment it is given and otherwise runs the generic tile
  * kernel (any filter length <= B200W_MAX_TAPS, any mode, any layout).  The *_generic symbols take the

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     '-Xcompiler', '-fPIC',
     '--expt-relaxed-constexpr',
 ]
-LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static']
+LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static', '-ldl']
 
 
 def sources():

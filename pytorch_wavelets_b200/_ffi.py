@@ -26,7 +26,9 @@ SYMBOLS = [
     'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1', 'b200w_dwt_forward',
 ]
 KERNEL_ENTRIES = SYMBOLS[5:13]
-SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + ['b200w_dwt_forward_workspace']
+SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + [
+    'b200w_dwt_forward_workspace', 'b200w_comm_unique_id', 'b200w_comm_init', 'b200w_comm_destroy', 'b200w_allgather',
+    'b200w_comm_last_error']
 
 
 class B200WaveError(RuntimeError):
@@ -64,6 +66,11 @@ def lib():
                                         pf, pf, c_int, pf, pf, c_int, c_int, c_vp, c_ll, c_vp]
         L.b200w_dwt_forward_workspace.argtypes = [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
         L.b200w_dwt_forward_workspace.restype = c_ll
+        L.b200w_comm_unique_id.argtypes = [c_vp]
+        L.b200w_comm_init.argtypes = [ctypes.POINTER(c_vp), c_int, c_int, c_vp]
+        L.b200w_comm_destroy.argtypes = [c_vp]
+        L.b200w_allgather.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp]
+        L.b200w_comm_last_error.restype = ctypes.c_char_p
         for s in KERNEL_ENTRIES:
             getattr(L, s + '_generic').argtypes = getattr(L, s).argtypes
         _lib = L
