@@ -91,8 +91,6 @@ def _set_host_threads(n):
     """All host cores for the OpenMP oracle, whatever the launcher exported (torchrun presets OMP_NUM_THREADS=1)."""
     import ctypes
     os.environ['OMP_NUM_THREADS'] = str(n)
-    os.environ['OMP_PROC_BIND'] = 'spread'
-    os.environ['OMP_PLACES'] = 'cores'
     try:
         os.sched_setaffinity(0, range(os.cpu_count() or 1))
     except Exception:
@@ -103,9 +101,11 @@ def _set_host_threads(n):
         pass
 
 
-def cpu_sample(dwt_n=8, dtcwt_n=8, reps=3):
+def cpu_sample(dwt_n=8, dtcwt_n=None, reps=3):
     import numpy as np
     cores = os.cpu_count() or 1
+    if dtcwt_n is None:   # the oracle parallelises over planes (3 per image): give every host thread one
+        dtcwt_n = max(8, min(64, (cores + 2) // 3))
     _set_host_threads(cores)
     from oracle import oracle as orc
     from pytorch_wavelets_b200 import wavelets
@@ -158,7 +158,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     r = None
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(dwt_n=8, dtcwt_n=8, reps=3)
+        r = cpu_sample(dwt_n=8, reps=3)
         if i >= args.warmup:
             vals.append(r)
         if time.perf_counter() - t0 > 120:  # keep the whole arm within a few minutes

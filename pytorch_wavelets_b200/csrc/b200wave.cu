@@ -269,20 +269,22 @@ static void dwt_ws_layout(int planes, int H, int W, int J, int Lw, int Lh, int m
 //   kPyramidFirst level 1 in the pyramid kernel (TMA loads, bulk stores, writes the padded low-pass into the
 //                 workspace), deeper levels one streaming kernel each
 //   kLevels       one K1 launch per level
-// Measured on B200 (profiles/r02_notes.md): the pyramid kernel is register / shared-memory bound to 2 CTAs per SM
-// when it carries more than one level, which costs more than the hand-off traffic it saves on large planes, while
-// its single-level form (4 CTAs per SM) beats the streaming kernel; small planes favour the single launch.
+// Measured on B200 (profiles/r02_notes.md, tools/policy_probe.py; 268 Mpix per call, J = 3, db4): with more than one
+// level in the kernel an 8-warp CTA (planes narrower than ~700 columns) is register / shared-memory bound to 2 per SM,
+// which costs more than the hand-off traffic it saves (512^2: 0.73 vs 0.68 ms, 256^2: 1.34 vs 0.87 ms), while the
+// single-level form runs 3 CTAs per SM and beats the streaming kernel (1.67 vs 1.97 ms); from 1024 columns up a CTA
+// has enough level-1 warps and the single launch wins (1024^2: 0.71 vs 0.77 ms).
 enum DwtPolicy { kLevels = 0, kPyramidFirst = 1, kPyramidAll = 2 };
 
-#ifndef B200W_PYR_FUSE_ALL_MAX_SIDE
-#define B200W_PYR_FUSE_ALL_MAX_SIDE 0   /* planes up to this side use kPyramidAll (0: never, set from measurements) */
+#ifndef B200W_PYR_FUSE_ALL_MIN_WIDTH
+#define B200W_PYR_FUSE_ALL_MIN_WIDTH 1024   /* planes at least this wide run every level in the pyramid kernel */
 #endif
 
 static DwtPolicy dwt_policy(PyrParams& pp, const float* x, long long xps, int xpitch, int planes, int H, int W, int J,
                             int Lw, int Lh, int mode, bool generic) {
   if (generic || Lw != Lh) return kLevels;
-  const bool small = (H <= B200W_PYR_FUSE_ALL_MAX_SIDE && W <= B200W_PYR_FUSE_ALL_MAX_SIDE);
-  if ((J == 1 || small) && fast::plan_dwt_pyramid(pp, x, xps, xpitch, planes, H, W, J, Lw, mode, 0) == 0)
+  const bool wide = (W >= B200W_PYR_FUSE_ALL_MIN_WIDTH);
+  if ((J == 1 || wide) && fast::plan_dwt_pyramid(pp, x, xps, xpitch, planes, H, W, J, Lw, mode, 0) == 0)
     return kPyramidAll;
   if (J >= 2) {
     const int wo = coeff_len(W, Lw, mode);

@@ -48,7 +48,6 @@ int launch_dwt_pyramid(const PyrParams& p, cudaStream_t stream) {
     case 8: return launch_pyramid<8>(p, stream);
     case 10: return launch_pyramid<10>(p, stream);
     case 12: return launch_pyramid<12>(p, stream);
-    case 16: return launch_pyramid<16>(p, stream);
     default: return kNoFastPath;
   }
 }

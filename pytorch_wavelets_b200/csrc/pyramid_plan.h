@@ -97,7 +97,7 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
                         const void* x, int max_smem_bytes, int nslot = 4, int split = 1, int extra_in = 1,
                         int ll_pitch = 0) {
   if (J < 1 || J > kPyrMaxLevels) return 1;
-  if (L < 2 || (L & 1) || L > 16) return 1;
+  if (L < 2 || (L & 1) || L > 12) return 1;   // (longer filters: the register window no longer fits 128 registers)
   if (mode != B200W_MODE_ZERO && mode != B200W_MODE_SYMMETRIC && mode != B200W_MODE_REFLECT) return 1;
   // TMA bulk row copies: 16-byte aligned source rows of a multiple of 16 bytes
   if ((W & 3) || (xpitch & 3) || (xps & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;

@@ -1,0 +1,174 @@
+"""GPU tests (-m gpu) of the whole-transform entry point b200w_dwt_forward (fused pyramid kernel / level-1 pyramid +
+streaming levels / level kernels) and parity at the FULL BASELINE shapes (sampled planes against the oracle)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_wavelets_b200 as pw
+from oracle import oracle as orc
+from pytorch_wavelets_b200 import _ffi
+from pytorch_wavelets_b200.dwt import lowlevel
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _n(t):
+    return t.detach().cpu().numpy()
+
+
+def _per_level(f, x, J, mode):
+    m = lowlevel.mode_to_int(mode)
+    ll, yh = x, []
+    for j in range(J):
+        ll, h = lowlevel.afb2d_level(ll, f.h0_col, f.h1_col, f.h0_row, f.h1_row, m, pad_ll=(j < J - 1))
+        yh.append(h)
+    return ll.contiguous(), yh
+
+
+CASES = [((2, 3, 64, 64), 3, 'db4', 'symmetric'), ((2, 3, 64, 64), 1, 'db4', 'zero'), ((1, 2, 96, 128), 3, 'db4', 'reflect'),
+         ((2, 2, 99, 100), 2, 'db2', 'symmetric'), ((1, 3, 130, 260), 4, 'db1', 'zero'), ((2, 2, 200, 256), 3, 'db3', 'symmetric'),
+         ((1, 2, 128, 128), 1, 'db5', 'symmetric'), ((1, 2, 160, 192), 2, 'db6', 'reflect'), ((1, 2, 256, 256), 1, 'db8', 'zero'),
+         ((3, 5, 512, 512), 3, 'db4', 'symmetric'), ((1, 1, 1024, 1024), 3, 'db4', 'symmetric'), ((2, 1, 72, 1024), 2, 'db2', 'zero'), ((1, 2, 37, 52), 2, 'db4', 'zero'),
+         ((2, 2, 64, 64), 2, 'db4', 'periodization'), ((1, 2, 40, 66), 2, 'db3', 'periodic'), ((1, 1, 2048, 2048), 1, 'db4', 'symmetric')]
+
+
+@pytest.mark.parametrize('shape,J,wave,mode', CASES)
+def test_dwt_forward_entry_matches_level_kernels_and_oracle(shape, J, wave, mode):
+    """Whatever route the policy picks (one pyramid launch, pyramid + streaming levels, level kernels), the result is
+    bit-identical to the level-by-level streaming path and to the oracle (same FMA order everywhere)."""
+    torch.manual_seed(5)
+    x = torch.randn(*shape, device=DEV)
+    f = pw.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+    yl, yh = f(x)
+    assert yl.is_contiguous() and all(h.is_contiguous() for h in yh)
+    rl, rh = _per_level(f, x, J, mode)
+    assert torch.equal(yl, rl) and all(torch.equal(a, b) for a, b in zip(yh, rh))
+    if x.numel() <= 4 * 512 * 512:
+        hf = [_n(b) for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+        oyl, oyh = orc.dwt_forward(_n(x), hf, J, mode)
+        assert np.array_equal(_n(yl), oyl) and all(np.array_equal(_n(a), b) for a, b in zip(yh, oyh))
+
+
+def test_pyramid_kernel_is_what_runs_for_the_baseline_shape():
+    """BASELINE configs[1] shape: J = 1 needs no workspace (one fused launch); J = 3 runs level 1 in the pyramid kernel
+    (workspace = the two padded inter-level low-passes)."""
+    L = _ffi.lib()
+    x = torch.randn(4, 32, 512, 512, device=DEV)
+    w1 = L.b200w_dwt_forward_workspace(x.data_ptr(), 512 * 512, 512, 128, 512, 512, 1, 8, 8, 1)
+    w3 = L.b200w_dwt_forward_workspace(x.data_ptr(), 512 * 512, 512, 128, 512, 512, 3, 8, 8, 1)
+    assert w1 == 0
+    assert w3 == 4 * 128 * (259 * 288 + 133 * 160)
+    # unaligned rows cannot be staged by the TMA engine: level kernels (still correct, checked above for 37x52)
+    assert L.b200w_dwt_forward_workspace(x.data_ptr() + 4, 512 * 512, 512, 128, 512, 512, 1, 8, 8, 1) == 0
+
+
+def test_dwt_forward_rejects_a_short_workspace_and_bad_arguments():
+    L = _ffi.lib()
+    x = torch.randn(1, 2, 64, 64, device=DEV)
+    f = pw.DWTForward(J=2, wave='db4', mode='symmetric')
+    taps = [_ffi.host_taps(b) for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    yh = [torch.empty(1, 2, 3, 35, 35, device=DEV), torch.empty(1, 2, 3, 21, 21, device=DEV)]
+    yl = torch.empty(1, 2, 21, 21, device=DEV)
+    ptrs = (ctypes.c_void_p * 2)(*[t.data_ptr() for t in yh])
+    need = L.b200w_dwt_forward_workspace(x.data_ptr(), 64 * 64, 64, 2, 64, 64, 2, 8, 8, 1)
+    assert need > 0
+    args = lambda ws, n, mode=1: (x.data_ptr(), 64 * 64, 64, 2, 64, 64, 2, yl.data_ptr(), ptrs, taps[0].ptr, taps[1].ptr, 8,
+                                  taps[2].ptr, taps[3].ptr, 8, mode, ws, n, None)
+    assert L.b200w_dwt_forward(*args(None, 0)) == -3                      # B200W_EARG: workspace missing
+    ws = torch.empty(need // 4, device=DEV)
+    assert L.b200w_dwt_forward(*args(ws.data_ptr(), need - 4)) == -3
+    assert L.b200w_dwt_forward(*args(ws.data_ptr(), need, mode=3)) == -1  # B200W_EMODE ('constant' is not a bank mode)
+    assert L.b200w_dwt_forward(*args(ws.data_ptr(), need)) == 0
+    torch.cuda.synchronize()
+    ref = f.to(DEV)(x)
+    assert torch.equal(yl, ref[0]) and torch.equal(yh[0], ref[1][0]) and torch.equal(yh[1], ref[1][1])
+
+
+def test_dwt_pyramid_function_backward_matches_level_chain():
+    """DWTPyramid.backward = the reference's chain of AFB2D.backward calls."""
+    torch.manual_seed(7)
+    x = torch.randn(2, 2, 64, 96, device=DEV)
+    f = pw.DWTForward(J=3, wave='db3', mode='zero').to(DEV)
+    xa = x.clone().requires_grad_(True)
+    yl, yh = f(xa)
+    gl, gh = torch.randn_like(yl), [torch.randn_like(h) for h in yh]
+    (yl * gl).sum().backward(retain_graph=True) if False else None
+    loss = (yl * gl).sum() + sum((h * g).sum() for h, g in zip(yh, gh))
+    loss.backward()
+    xb = x.clone().requires_grad_(True)
+    m = lowlevel.mode_to_int('zero')
+    ll, hs = xb, []
+    for j in range(3):
+        ll, h = lowlevel.AFB2D.apply(ll, f.h0_col, f.h1_col, f.h0_row, f.h1_row, m)
+        hs.append(h)
+    loss_b = (ll * gl).sum() + sum((h * g).sum() for h, g in zip(hs, gh))
+    loss_b.backward()
+    assert (xa.grad - xb.grad).abs().max().item() <= 1e-5 * xb.grad.abs().max().item()
+
+
+# ---------------------------------------------------------------- full BASELINE shapes, sampled planes vs the oracle
+
+def _sample(n, k=4, seed=0):
+    rng = np.random.default_rng(seed)
+    return sorted(set([0, n - 1] + [int(v) for v in rng.integers(1, max(2, n - 1), size=k - 2)]))
+
+
+def test_full_shape_config2_dwt_forward_and_inverse():
+    """BASELINE configs[1]: 128x32x512x512, J=3, db4, symmetric -- the bench launch geometry (4096 planes)."""
+    torch.manual_seed(21)
+    x = torch.randn(128, 32, 512, 512, device=DEV)
+    f = pw.DWTForward(J=3, wave='db4', mode='symmetric').to(DEV)
+    g = pw.DWTInverse(wave='db4', mode='symmetric').to(DEV)
+    yl, yh = f(x)
+    y = g((yl, yh))
+    hf = [_n(b) for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    gf = [_n(b) for b in (g.g0_col, g.g1_col, g.g0_row, g.g1_row)]
+    for p in _sample(128 * 32):
+        n, c = divmod(p, 32)
+        oyl, oyh = orc.dwt_forward(_n(x[n:n + 1, c:c + 1]), hf, 3, 'symmetric')
+        assert np.array_equal(_n(yl[n:n + 1, c:c + 1]), oyl), 'plane %d' % p            # bit-equal analysis
+        for a, b in zip(yh, oyh):
+            assert np.array_equal(_n(a[n:n + 1, c:c + 1]), b), 'plane %d' % p
+        oy = orc.dwt_inverse(oyl, oyh, gf, 'symmetric')
+        util.assert_close(_n(y[n:n + 1, c:c + 1]), oy, util.RTOL_F32, 'inverse plane %d' % p)
+    del yl, yh, y
+
+
+def test_full_shape_config3_dtcwt_forward_and_inverse():
+    """BASELINE configs[2]: 64x3x1024x1024, J=3, near_sym_a / qshift_a."""
+    torch.manual_seed(22)
+    x = torch.randn(64, 3, 1024, 1024, device=DEV)
+    f = pw.DTCWTForward(J=3).to(DEV)
+    g = pw.DTCWTInverse().to(DEV)
+    yl, yh = f(x)
+    y = g((yl, yh))
+    l1 = (_n(f.h0o), _n(f.h1o))
+    qs = (_n(f.h0a), _n(f.h0b), _n(f.h1a), _n(f.h1b))
+    gl1 = (_n(g.g0o), _n(g.g1o))
+    gqs = (_n(g.g0a), _n(g.g0b), _n(g.g1a), _n(g.g1b))
+    for p in _sample(64 * 3, seed=1):
+        n, c = divmod(p, 3)
+        oyl, oyh = orc.dtcwt_forward(_n(x[n:n + 1, c:c + 1]), l1, qs, 3)
+        util.assert_close(_n(yl[n:n + 1, c:c + 1]), oyl, util.RTOL_F32, 'yl plane %d' % p)
+        for j, (a, b) in enumerate(zip(yh, oyh)):
+            util.assert_close(_n(a[n:n + 1, c:c + 1]), b, util.RTOL_F32, 'yh%d plane %d' % (j, p))
+        oy = orc.dtcwt_inverse(oyl, oyh, gl1, gqs)
+        util.assert_close(_n(y[n:n + 1, c:c + 1]), oy, util.RTOL_F32, 'inverse plane %d' % p)
+
+
+def test_full_shape_config4_scatlayer_x2():
+    """BASELINE configs[3]: ScatLayer x2 on 256x3x256x256 -- sampled images against the oracle."""
+    torch.manual_seed(23)
+    x = torch.randn(256, 3, 256, 256, device=DEV)
+    s1, s2 = pw.ScatLayer().to(DEV), pw.ScatLayer().to(DEV)
+    with torch.no_grad():
+        z = s2(s1(x))
+    assert tuple(z.shape) == (256, 147, 64, 64)
+    lv = (_n(s1.h0o.data), _n(s1.h1o.data))
+    for n in _sample(256, seed=2):
+        o = orc.scat_layer(orc.scat_layer(_n(x[n:n + 1]), lv, 'symmetric', 1e-2), lv, 'symmetric', 1e-2)
+        util.assert_close(_n(z[n:n + 1]), o, util.RTOL_F32, 'image %d' % n)
