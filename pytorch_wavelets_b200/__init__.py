@@ -2,7 +2,7 @@
 fbcotter/pytorch_wavelets, behind the reference's nn.Module API.
 
 Same export list and aliases as the reference package (``pytorch_wavelets/__init__.py:1-36``) for the
-classes on the hot path; the 1-D DWT, SWT and ``ScatLayerj2`` are out of scope.
+classes on the hot path and its direct callers.
 Every transform runs in hand-written CUDA kernels through the C ABI of ``libb200wave.so``; there is no
 CPU or eager fallback.
 """
@@ -19,12 +19,13 @@ __all__ = [
     'DWT2D',
     'IDWT2D',
     'ScatLayer',
+    'ScatLayerj2',
 ]
 
 from pytorch_wavelets_b200._version import __version__
 from pytorch_wavelets_b200.dtcwt.transform2d import DTCWTForward, DTCWTInverse
 from pytorch_wavelets_b200.dwt.transform2d import DWTForward, DWTInverse
-from pytorch_wavelets_b200.scatternet import ScatLayer
+from pytorch_wavelets_b200.scatternet import ScatLayer, ScatLayerj2
 
 # aliases, as in the reference
 DTCWT = DTCWTForward

@@ -1,1 +1,1 @@
-from pytorch_wavelets_b200.scatternet.layers import ScatLayer  # noqa: F401
+from pytorch_wavelets_b200.scatternet.layers import ScatLayer, ScatLayerj2  # noqa: F401

@@ -86,6 +86,38 @@ def scat_case(name, shape, biort, mode, seed, magbias=1e-2):
          mode=mode, biort=biort, magbias=magbias)
 
 
+def scat_variant_case(name, shape, kind, seed, biort='near_sym_a', qshift='qshift_a', mode='symmetric',
+                      combine_colour=False, magbias=1e-2):
+    """ScatLayer variants of SURVEY 8(f)2: combine_colour, the 3-filter *_bp ("rot") filters, ScatLayerj2; the
+    gradient with respect to the input is stored too (it exercises the reference's hand-written backward)."""
+    torch.manual_seed(seed)
+    x = torch.randn(*shape, requires_grad=True)
+    if kind == 'j1':
+        s = ref.ScatLayer(biort=biort, mode=mode, magbias=magbias, combine_colour=combine_colour)
+    else:
+        s = ref.ScatLayerj2(biort=biort, qshift=qshift, mode=mode, magbias=magbias, combine_colour=combine_colour)
+    z = s(x)
+    torch.manual_seed(seed + 1000)
+    g = torch.randn_like(z)
+    (z * g).sum().backward()
+    save(name, x=x.detach(), z=z.detach(), g=g, dx=x.grad, kind=kind, biort=biort, qshift=qshift, mode=mode,
+         combine_colour=int(combine_colour), magbias=magbias)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'scatvar':
+    scat_variant_case('scatv_j1_cc_32', (2, 3, 32, 32), 'j1', 60, combine_colour=True)
+    scat_variant_case('scatv_j1_bp_32', (1, 2, 32, 32), 'j1', 61, biort='near_sym_b_bp')
+    scat_variant_case('scatv_j1_bp_cc_zero_30x32', (1, 3, 30, 32), 'j1', 62, biort='near_sym_b_bp', mode='zero',
+                      combine_colour=True)
+    scat_variant_case('scatv_j2_a_32', (2, 2, 32, 32), 'j2', 63)
+    scat_variant_case('scatv_j2_a_cc_40x36', (1, 3, 40, 36), 'j2', 64, combine_colour=True)
+    scat_variant_case('scatv_j2_bp_32', (1, 2, 32, 32), 'j2', 65, biort='near_sym_b_bp', qshift='qshift_b_bp')
+    scat_variant_case('scatv_j2_bp_cc_32', (1, 3, 32, 32), 'j2', 66, biort='near_sym_b_bp', qshift='qshift_b_bp',
+                      combine_colour=True)
+    scat_variant_case('scatv_j2_b_34x44', (1, 1, 34, 44), 'j2', 67, biort='near_sym_b', qshift='qshift_b')
+    # (ScatLayerj2 with mode='zero' raises NotImplementedError in the reference: rowdfilt, dtcwt/lowlevel.py:142)
+    sys.exit(0)
+
 if __name__ == '__main__':
     # BASELINE.json config 1: DWTForward J=1 db4 zero on randn(4,3,64,64) -- the bit-check case
     dwt_case('dwt_c1_db4_zero_J1', (4, 3, 64, 64), 1, 'db4', 'zero', 0)
