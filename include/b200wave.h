@@ -128,6 +128,20 @@ int b200w_dwt_sfb2d(const float* ll, long long ll_plane_stride, int ll_pitch,
                     int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 1-D DWT levels.                           Replace AFB1D.forward / SFB1D.forward, reference dwt/lowlevel.py:388-404,
+ *     717-729 (afb1d / sfb1d along the last dimension; the level loops are DWT1DForward / DWT1DInverse,
+ *     dwt/transform1d.py:44-65, 97-115).  Same modes, tap conventions and length rules as K1 / K2.
+ *   b200w_dwt_afb1d: x (rows, N) with row pitch x_pitch -> lo, hi (rows, K) contiguous, K = b200w_dwt_coeff_len(N, L, mode)
+ *   b200w_dwt_sfb1d: lo, hi (rows, K) contiguous (hi may be NULL = zeros) -> y (rows, Nout) contiguous,
+ *                    Nout <= b200w_dwt_rec_len(K, L, mode) (smaller = the crop of AFB1D.backward, :406-424)
+ * Each also computes the other's backward pass when given the same stored filters.
+ */
+int b200w_dwt_afb1d(const float* x, long long x_pitch, int rows, int N, float* lo, float* hi,
+                    const float* f0, const float* f1, int L, int mode, void* stream);
+int b200w_dwt_sfb1d(const float* lo, const float* hi, int rows, int K, float* y, int Nout,
+                    const float* g0, const float* g1, int L, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DTCWT.  "highs" is the reference's 6-D complex band-pass tensor; because o_dim / ri_dim are
  * configurable (dtcwt/transform_funcs.py:10-58) it is described by six ELEMENT strides
  * hs[6] = {n, c, orientation, row, col, real/imag}.  Default layout (N,C,6,H/2,W/2,2) is the

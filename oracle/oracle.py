@@ -128,6 +128,57 @@ def dwt_sfb2d(ll, highs, gh_lo, gh_hi, gw_lo, gw_hi, mode, out_hw=None):
     return y
 
 
+def dwt_afb1d(x, f0, f1, mode):
+    """AFB1D.forward (dwt/lowlevel.py:388-404): x (N,C,L) -> lo, hi (N,C,K)."""
+    x = np.ascontiguousarray(x)
+    sfx, _ = _sfx(x.dtype)
+    N, C, n = x.shape
+    m = mode_int(mode)
+    f0, f1 = _taps(f0, x.dtype), _taps(f1, x.dtype)
+    K = coeff_len(n, f0.size, m)
+    lo, hi = np.empty((N, C, K), x.dtype), np.empty((N, C, K), x.dtype)
+    rc = getattr(lib(), 'orc_dwt_afb1d' + sfx)(_p(x), ctypes.c_longlong(n), N * C, n, _p(lo), _p(hi), _p(f0), _p(f1),
+                                               f0.size, m)
+    _check(rc, 'orc_dwt_afb1d')
+    return lo, hi
+
+
+def dwt_sfb1d(lo, hi, g0, g1, mode, out_len=None):
+    """SFB1D.forward (dwt/lowlevel.py:717-729): lo, hi (N,C,K) -> y (N,C,rec_len); hi may be None (zeros)."""
+    lo = np.ascontiguousarray(lo)
+    sfx, _ = _sfx(lo.dtype)
+    N, C, K = lo.shape
+    m = mode_int(mode)
+    g0, g1 = _taps(g0, lo.dtype), _taps(g1, lo.dtype)
+    n = rec_len(K, g0.size, m) if out_len is None else int(out_len)
+    if hi is not None:
+        hi = np.ascontiguousarray(hi)
+    y = np.empty((N, C, n), lo.dtype)
+    rc = getattr(lib(), 'orc_dwt_sfb1d' + sfx)(_p(lo), _p(hi), N * C, K, _p(y), n, _p(g0), _p(g1), g0.size, m)
+    _check(rc, 'orc_dwt_sfb1d')
+    return y
+
+
+def dwt1d_forward(x, filts, J, mode):
+    """DWT1DForward.forward (dwt/transform1d.py:44-65); filts = stored (h0, h1)."""
+    x0, highs = x, []
+    for _ in range(J):
+        x0, x1 = dwt_afb1d(x0, filts[0], filts[1], mode)
+        highs.append(x1)
+    return x0, highs
+
+
+def dwt1d_inverse(yl, yh, filts, mode):
+    """DWT1DInverse.forward (dwt/transform1d.py:97-115): None band-passes are zeros; the low-pass loses its last
+    sample when it is one longer than the band-pass ('unpad')."""
+    x0 = yl
+    for x1 in yh[::-1]:
+        if x1 is not None and x0.shape[-1] > x1.shape[-1]:
+            x0 = x0[..., :-1]
+        x0 = dwt_sfb1d(x0, x1, filts[0], filts[1], mode)
+    return x0
+
+
 def highs_shape_strides(N, C, h, w, o_dim=2, ri_dim=-1):
     """Shape of the reference's 6-D band-pass tensor and its element strides in the order
     (n, c, orientation, row, col, real/imag).  Restates get_dimensions6, dtcwt/transform_funcs.py:32-58

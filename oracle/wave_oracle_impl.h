@@ -420,6 +420,30 @@ int FN(orc_ifilt)(const T* x, T* y, int planes, int H, int W, const T* ha, const
   return 0;
 }
 
+/* ---- 1-D DWT levels (AFB1D / SFB1D, dwt/lowlevel.py:368-424, 697-743): afb1d / sfb1d along the last dimension of
+ * `rows` independent signals ----------------------------------------------------------------------- */
+int FN(orc_dwt_afb1d)(const T* x, long long xpitch, int rows, int N, T* lo, T* hi, const T* f0, const T* f1, int L,
+                      int mode) {
+  if (!orc_mode_ok(mode)) return ORC_EMODE;
+  if (N < 1 || L < 1 || rows < 0) return ORC_ESIZE;
+  const int K = orc_coeff_len(N, L, mode);
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < rows; ++r)
+    FN(afb_line)(x + (long long)r * xpitch, 1, N, lo + (long long)r * K, 1, hi + (long long)r * K, 1, K, f0, f1, L, mode);
+  return 0;
+}
+
+int FN(orc_dwt_sfb1d)(const T* lo, const T* hi, int rows, int K, T* y, int Nout, const T* g0, const T* g1, int L,
+                      int mode) {
+  if (!orc_mode_ok(mode)) return ORC_EMODE;
+  if (K < 1 || L < 1 || rows < 0 || Nout < 1 || Nout > orc_rec_len(K, L, mode)) return ORC_ESIZE;
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < rows; ++r)
+    FN(sfb_line)(lo + (long long)r * K, 1, hi ? hi + (long long)r * K : (const T*)0, 1, K, y + (long long)r * Nout, 1,
+                 Nout, g0, g1, L, mode);
+  return 0;
+}
+
 /* ---- K1 / K2: DWT levels --------------------------------------------------------------------- */
 
 /* AFB2D.forward, dwt/lowlevel.py:336-347: afb1d along W (dim=3) then along H (dim=2) on the

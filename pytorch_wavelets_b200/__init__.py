@@ -18,12 +18,17 @@ __all__ = [
     'IDWT',
     'DWT2D',
     'IDWT2D',
+    'DWT1DForward',
+    'DWT1DInverse',
+    'DWT1D',
+    'IDWT1D',
     'ScatLayer',
     'ScatLayerj2',
 ]
 
 from pytorch_wavelets_b200._version import __version__
 from pytorch_wavelets_b200.dtcwt.transform2d import DTCWTForward, DTCWTInverse
+from pytorch_wavelets_b200.dwt.transform1d import DWT1DForward, DWT1DInverse
 from pytorch_wavelets_b200.dwt.transform2d import DWTForward, DWTInverse
 from pytorch_wavelets_b200.scatternet import ScatLayer, ScatLayerj2
 
@@ -34,3 +39,5 @@ DWT = DWTForward
 IDWT = DWTInverse
 DWT2D = DWT
 IDWT2D = IDWT
+DWT1D = DWT1DForward
+IDWT1D = DWT1DInverse

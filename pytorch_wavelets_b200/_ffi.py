@@ -27,7 +27,7 @@ SYMBOLS = [
 ]
 KERNEL_ENTRIES = SYMBOLS[5:13]
 SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + [
-    'b200w_dwt_forward_workspace', 'b200w_comm_unique_id', 'b200w_comm_init', 'b200w_comm_destroy', 'b200w_allgather',
+    'b200w_dwt_forward_workspace', 'b200w_dwt_afb1d', 'b200w_dwt_sfb1d', 'b200w_comm_unique_id', 'b200w_comm_init', 'b200w_comm_destroy', 'b200w_allgather',
     'b200w_comm_last_error']
 
 
@@ -66,6 +66,8 @@ def lib():
                                         pf, pf, c_int, pf, pf, c_int, c_int, c_vp, c_ll, c_vp]
         L.b200w_dwt_forward_workspace.argtypes = [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
         L.b200w_dwt_forward_workspace.restype = c_ll
+        L.b200w_dwt_afb1d.argtypes = [c_vp, c_ll, c_int, c_int, c_vp, c_vp, pf, pf, c_int, c_int, c_vp]
+        L.b200w_dwt_sfb1d.argtypes = [c_vp, c_vp, c_int, c_int, c_vp, c_int, pf, pf, c_int, c_int, c_vp]
         L.b200w_comm_unique_id.argtypes = [c_vp]
         L.b200w_comm_init.argtypes = [ctypes.POINTER(c_vp), c_int, c_int, c_vp]
         L.b200w_comm_destroy.argtypes = [c_vp]

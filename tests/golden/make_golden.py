@@ -104,6 +104,37 @@ def scat_variant_case(name, shape, kind, seed, biort='near_sym_a', qshift='qshif
          combine_colour=int(combine_colour), magbias=magbias)
 
 
+def dwt1d_case(name, shape, J, wave, mode, seed):
+    torch.manual_seed(seed)
+    x = torch.randn(*shape)
+    f = ref.DWT1DForward(J=J, wave=wave, mode=mode)
+    i = ref.DWT1DInverse(wave=wave, mode=mode)
+    yl, yh = f(x)
+    y = i((yl, yh))
+    yh_drop = list(yh)
+    yh_drop[0] = None
+    y_drop = i((yl, yh_drop))
+    d = dict(x=x, yl=yl, y=y, y_drop0=y_drop, J=J, mode=mode, wave=wave)
+    for j, h in enumerate(yh):
+        d['yh%d' % j] = h
+    d.update(bufs(f, ['h0', 'h1']))
+    d.update(bufs(i, ['g0', 'g1']))
+    save(name, **d)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'extra':
+    dtcwt_case('dtcwt_b_32_J3_96x64', (1, 1, 96, 64), 3, 'near_sym_b', 'qshift_32', 2, -1, 'symmetric', 90)
+    sys.exit(0)
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'dwt1d':
+    k = 80
+    for mode in ['zero', 'symmetric', 'reflect', 'periodic', 'periodization']:
+        dwt1d_case('dwt1d_db4_%s_J3_200' % mode, (2, 3, 200), 3, 'db4', mode, k); k += 1
+        dwt1d_case('dwt1d_db3_%s_J2_77' % mode, (1, 2, 77), 2, 'db3', mode, k); k += 1
+    dwt1d_case('dwt1d_db1_zero_J4_1000', (1, 1, 1000), 4, 'db1', 'zero', k); k += 1
+    dwt1d_case('dwt1d_db8_symmetric_J2_513', (2, 1, 513), 2, 'db8', 'symmetric', k); k += 1
+    sys.exit(0)
+
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'scatvar':
     scat_variant_case('scatv_j1_cc_32', (2, 3, 32, 32), 'j1', 60, combine_colour=True)
     scat_variant_case('scatv_j1_bp_32', (1, 2, 32, 32), 'j1', 61, biort='near_sym_b_bp')
