@@ -25,7 +25,9 @@ __device__ __forceinline__ void q2c_emit(float a, float b, float c, float d, flo
   store_cplx(hq, so, sr, vec, o2, __fadd_rn(a, d), __fsub_rn(b, c));
 }
 
-// ScatLayer epilogue for one subband quad: smoothed magnitudes of w1 / w2 (+ optional re/r, im/r)
+// ScatLayer epilogue for one subband quad: smoothed magnitudes of w1 / w2 (+ re/r, im/r when DERIV: the tensors the
+// backward pass needs -- a separate instantiation, so the inference kernel carries no division code)
+template <bool DERIV>
 __device__ __forceinline__ void scat_emit(float a, float b, float c, float d, const DtParams& p, long long zbase,
                                           long long dbase, long long ostride, int o1, int o2) {
   a = __fmul_rn(a, kInvSqrt2); b = __fmul_rn(b, kInvSqrt2);
@@ -38,7 +40,7 @@ __device__ __forceinline__ void scat_emit(float a, float b, float c, float d, co
     const float rr = __fmul_rn(re[k], re[k]), ii = __fmul_rn(im[k], im[k]);
     const float r = __fsqrt_rn(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
     __stcs(p.z + zbase + (1 + os[k]) * ostride, __fsub_rn(r, p.magbias));
-    if (p.dre) {
+    if (DERIV) {
       __stcs(p.dre + dbase + os[k] * ostride, __fdiv_rn(re[k], r));
       __stcs(p.dim + dbase + os[k] * ostride, __fdiv_rn(im[k], r));
     }
@@ -66,11 +68,14 @@ struct J1Cfg {
   using Loader = StripLoader<2, SW, NS, NFIX>;
 };
 
-template <int L0, int L1, bool SCAT, int U>
+// One stage of the two passes.  The outputs of the column pass (one 2x2 quad per band and column pair) are handed back
+// in registers: the epilogue (stores / q2c / ScatLayer magnitudes) does not depend on the window position U, so it lives
+// once in the kernel's main loop instead of once per unrolled copy of the stage (instruction-cache footprint).
+struct J1Quads { float vll[2][2], vlh[2][2], vhl[2][2], vhh[2][2]; };   // [dr][o]
+
+template <int L0, int L1, int U>
 __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, float2 (&w)[J1Cfg<L0, L1>::WR][2],
-                                         bool emit, float*& ll_ptr, float*& hq,
-                                         long long& zoff, bool colvalid, bool vec, long long zplane, long long dplane,
-                                         long long ostride) {
+                                         bool emit, J1Quads& v) {
   using C = J1Cfg<L0, L1>;
   constexpr int WR = C::WR;
   // row pass on the two staged rows; window entries are {low-pass, high-pass} pairs (packed FMA where both filters
@@ -80,8 +85,8 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
     float x[2 * C::NV2];
 #pragma unroll
     for (int q = 0; q < C::NV2; ++q) {
-      const float2 v = *reinterpret_cast<const float2*>(s0 + r * C::SW + 2 * q);
-      x[2 * q] = v.x; x[2 * q + 1] = v.y;
+      const float2 t = *reinterpret_cast<const float2*>(s0 + r * C::SW + 2 * q);
+      x[2 * q] = t.x; x[2 * q + 1] = t.y;
     }
     const int S = (2 * U + r) % WR;
 #pragma unroll
@@ -100,7 +105,6 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
     }
   }
   if (emit) {
-    float vll[2][2], vlh[2][2], vhl[2][2], vhh[2][2];  // [dr][o]
 #pragma unroll
     for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
@@ -116,47 +120,26 @@ __device__ __forceinline__ void j1_stage(const DtParams& p, const float* s0, flo
           const int sl = (2 * U + dr - C::M - C::M1 + j + 4 * WR) % WR;
           bd = ffma2_s(p.f1.t[j], w[sl][o], bd);
         }
-        vll[dr][o] = ac.x; vlh[dr][o] = bd.x; vhl[dr][o] = ac.y; vhh[dr][o] = bd.y;
+        v.vll[dr][o] = ac.x; v.vlh[dr][o] = bd.x; v.vhl[dr][o] = ac.y; v.vhh[dr][o] = bd.y;
       }
-    if (colvalid) {
-      if (!SCAT) {
-        store2(ll_ptr, vll[0][0], vll[0][1], 2, false);
-        store2(ll_ptr + p.outpitch, vll[1][0], vll[1][1], 2, false);
-        if (p.highs) {
-          const long long so = p.hs[2], sr = p.hs[5];
-          q2c_emit(vlh[0][0], vlh[0][1], vlh[1][0], vlh[1][1], hq, so, sr, vec, 0, 5);  // lh -> 15, 165
-          q2c_emit(vhh[0][0], vhh[0][1], vhh[1][0], vhh[1][1], hq, so, sr, vec, 1, 4);  // hh -> 45, 135
-          q2c_emit(vhl[0][0], vhl[0][1], vhl[1][0], vhl[1][1], hq, so, sr, vec, 2, 3);  // hl -> 75, 105
-        }
-      } else {
-        float s = __fadd_rn(vll[0][0], vll[0][1]);
-        s = __fadd_rn(s, vll[1][0]);
-        s = __fadd_rn(s, vll[1][1]);
-        __stcs(p.z + zplane + zoff, __fmul_rn(s, 0.25f));
-        scat_emit(vlh[0][0], vlh[0][1], vlh[1][0], vlh[1][1], p, zplane + zoff, dplane + zoff, ostride, 0, 5);
-        scat_emit(vhh[0][0], vhh[0][1], vhh[1][0], vhh[1][1], p, zplane + zoff, dplane + zoff, ostride, 1, 4);
-        scat_emit(vhl[0][0], vhl[0][1], vhl[1][0], vhl[1][1], p, zplane + zoff, dplane + zoff, ostride, 2, 3);
-      }
-    }
-    ll_ptr += 2 * p.outpitch;
-    hq += p.hs[3];
-    zoff += (p.W >> 1);
   }
 }
 
-template <int L0, int L1, bool SCAT, int U>
+template <int L0, int L1, int U>
 __device__ __forceinline__ void j1_dispatch(int uu, const DtParams& p, const float* s0,
-                                            float2 (&w)[J1Cfg<L0, L1>::WR][2],
-                                            bool emit, float*& ll_ptr, float*& hq, long long& zoff, bool colvalid,
-                                            bool vec, long long zplane, long long dplane, long long ostride) {
+                                            float2 (&w)[J1Cfg<L0, L1>::WR][2], bool emit, J1Quads& v) {
   if constexpr (U < J1Cfg<L0, L1>::UNR) {
-    if (uu == U) j1_stage<L0, L1, SCAT, U>(p, s0, w, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
-    else j1_dispatch<L0, L1, SCAT, U + 1>(uu, p, s0, w, emit, ll_ptr, hq, zoff, colvalid, vec, zplane, dplane, ostride);
+    if (uu == U) j1_stage<L0, L1, U>(p, s0, w, emit, v);
+    else j1_dispatch<L0, L1, U + 1>(uu, p, s0, w, emit, v);
   }
 }
 
-template <int L0, int L1, bool SCAT>
-__global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+// SCAT: 0 = DTCWT level 1 (q2c), 1 = ScatLayer magnitudes, 2 = ScatLayer magnitudes + derivative tensors
+#ifndef B200W_J1_MINB
+#define B200W_J1_MINB 1
+#endif
+template <int L0, int L1, int SCAT>
+__global__ void __launch_bounds__(32, B200W_J1_MINB) fwd_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
                                                     int CH /* quad rows per chunk */) {
   using C = J1Cfg<L0, L1>;
   extern __shared__ __align__(16) float ring[];
@@ -205,14 +188,40 @@ __global__ void __launch_bounds__(32) fwd_j1_stream(const __grid_constant__ DtPa
   for (int t = 0; t < n_stage; ++t) {
     const float* stage = ld.acquire(t);
     ld.issue(t + C::NS - 1);
-    j1_dispatch<L0, L1, SCAT, 0>(uu, p, stage + 2 * lane, w, t >= C::PRO, ll_ptr, hq, zoff, colvalid, vec, zplane,
-                                 dplane, ostride);
+    const bool emit = (t >= C::PRO);
+    J1Quads v;
+    j1_dispatch<L0, L1, 0>(uu, p, stage + 2 * lane, w, emit, v);
     uu = (uu + 1 == C::UNR) ? 0 : uu + 1;
+    if (emit) {
+      if (colvalid) {
+        if (!SCAT) {
+          store2(ll_ptr, v.vll[0][0], v.vll[0][1], 2, false);
+          store2(ll_ptr + p.outpitch, v.vll[1][0], v.vll[1][1], 2, false);
+          if (p.highs) {
+            const long long so = p.hs[2], sr = p.hs[5];
+            q2c_emit(v.vlh[0][0], v.vlh[0][1], v.vlh[1][0], v.vlh[1][1], hq, so, sr, vec, 0, 5);  // lh -> 15, 165
+            q2c_emit(v.vhh[0][0], v.vhh[0][1], v.vhh[1][0], v.vhh[1][1], hq, so, sr, vec, 1, 4);  // hh -> 45, 135
+            q2c_emit(v.vhl[0][0], v.vhl[0][1], v.vhl[1][0], v.vhl[1][1], hq, so, sr, vec, 2, 3);  // hl -> 75, 105
+          }
+        } else {
+          float s = __fadd_rn(v.vll[0][0], v.vll[0][1]);
+          s = __fadd_rn(s, v.vll[1][0]);
+          s = __fadd_rn(s, v.vll[1][1]);
+          __stcs(p.z + zplane + zoff, __fmul_rn(s, 0.25f));
+          scat_emit<SCAT == 2>(v.vlh[0][0], v.vlh[0][1], v.vlh[1][0], v.vlh[1][1], p, zplane + zoff, dplane + zoff, ostride, 0, 5);
+          scat_emit<SCAT == 2>(v.vhh[0][0], v.vhh[0][1], v.vhh[1][0], v.vhh[1][1], p, zplane + zoff, dplane + zoff, ostride, 1, 4);
+          scat_emit<SCAT == 2>(v.vhl[0][0], v.vhl[0][1], v.vhl[1][0], v.vhl[1][1], p, zplane + zoff, dplane + zoff, ostride, 2, 3);
+        }
+      }
+      ll_ptr += 2 * p.outpitch;
+      hq += p.hs[3];
+      zoff += (p.W >> 1);
+    }
   }
   cp_async_wait<0>();
 }
 
-template <int L0, int L1, bool SCAT>
+template <int L0, int L1, int SCAT>
 inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
   using C = J1Cfg<L0, L1>;
   if (!aligned_plane(p.in, p.inps, p.inpitch)) return kNoFastPath;
@@ -230,7 +239,7 @@ inline int launch_j1_stream(const DtParams& p, cudaStream_t stream) {
   return 0;
 }
 
-template <bool SCAT>
+template <int SCAT>
 inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
   if (!SCAT && !p.highs) return kNoFastPath;  // skip_hps: low-pass only, generic kernel
   if ((long long)p.N * p.C == 0) return 0;
@@ -240,14 +249,16 @@ inline int try_launch_j1_any(const DtParams& p, cudaStream_t stream) {
   if (p.L0 == 5 && p.L1 == 3) return launch_j1_stream<5, 3, SCAT>(p, stream);   // legall
   if (p.L0 == 13 && p.L1 == 19) return launch_j1_stream<13, 19, SCAT>(p, stream);  // near_sym_b
   if (!SCAT) {  // synthesis filter pairs: the backward pass of the level-1 inverse
-    if (p.L0 == 7 && p.L1 == 9) return launch_j1_stream<7, 9, false>(p, stream);    // antonini
-    if (p.L0 == 3 && p.L1 == 5) return launch_j1_stream<3, 5, false>(p, stream);    // legall
-    if (p.L0 == 19 && p.L1 == 13) return launch_j1_stream<19, 13, false>(p, stream);  // near_sym_b
+    if (p.L0 == 7 && p.L1 == 9) return launch_j1_stream<7, 9, 0>(p, stream);    // antonini
+    if (p.L0 == 3 && p.L1 == 5) return launch_j1_stream<3, 5, 0>(p, stream);    // legall
+    if (p.L0 == 19 && p.L1 == 13) return launch_j1_stream<19, 13, 0>(p, stream);  // near_sym_b
   }
   return kNoFastPath;
 }
-int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<false>(p, stream); }
-int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<true>(p, stream); }
+int try_launch_fwd_j1(const DtParams& p, cudaStream_t stream) { return try_launch_j1_any<0>(p, stream); }
+int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) {
+  return (p.dre != nullptr) ? try_launch_j1_any<2>(p, stream) : try_launch_j1_any<1>(p, stream);
+}
 
 // ================================================================================================
 // K4 fast: DTCWT level >= 2 forward, q-shift filters of even length MQ.

@@ -32,7 +32,13 @@ __device__ unsigned long long g_pyr_prof[64];   // [role (0 producer, 1 writer, 
 #define PYR_FLUSH(role, lane) do {} while (0)
 #endif
 
-constexpr int kPyrSplitC = 1, kPyrNSlotC = 4;   // the shape the kernel is compiled for (plan_pyramid_best only offers it)
+#ifndef B200W_PYR_SPLIT
+#define B200W_PYR_SPLIT 1
+#endif
+#ifndef B200W_PYR_NSLOT
+#define B200W_PYR_NSLOT 4
+#endif
+constexpr int kPyrSplitC = B200W_PYR_SPLIT, kPyrNSlotC = B200W_PYR_NSLOT;   // the shape the kernel is compiled for (plan_pyramid_best only offers it)
 
 template <int L>
 struct PyrCfg {

@@ -137,6 +137,29 @@ def test_dwt_vs_oracle(mode, wave, J, shape):
     assert np.abs(_n(y)[:, :, :H, :W] - x.numpy()).max() < 2e-5
 
 
+@pytest.mark.parametrize('mode', ['zero', 'symmetric', 'periodization'])
+@pytest.mark.parametrize('wave', ['bior2.4', 'bior1.3', 'bior4.4', 'rbio3.3', 'sym4', 'sym5', 'coif1'])
+def test_dwt_other_families_vs_oracle(wave, mode):
+    """Wavelet families beyond dbN (the reference's tests use 'bior2.4', tests/test_dwt.py:37): zero-padded biorthogonal
+    banks, symlets, coif1 through the public modules against the oracle with the same taps."""
+    torch.manual_seed(2)
+    shape, J = (2, 3, 96, 120), 2
+    x = torch.randn(*shape)
+    f = pw.DWTForward(J=J, wave=wave, mode=mode)
+    i = pw.DWTInverse(wave=wave, mode=mode)
+    hf = [b.numpy() for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
+    gf = [b.numpy() for b in (i.g0_col, i.g1_col, i.g0_row, i.g1_row)]
+    oyl, oyh = orc.dwt_forward(x.numpy(), hf, J, mode)
+    f, i = f.to(DEV), i.to(DEV)
+    yl, yh = f(x.to(DEV))
+    assert np.array_equal(_n(yl), oyl), util.rel_err(_n(yl), oyl)
+    for j in range(J):
+        assert np.array_equal(_n(yh[j]), oyh[j]), util.rel_err(_n(yh[j]), oyh[j])
+    y = i((yl, yh))
+    util.assert_close(_n(y), orc.dwt_inverse(oyl, oyh, gf, mode), TOL, 'inverse')
+    assert np.abs(_n(y) - x.numpy()).max() < 2e-5
+
+
 def test_dwt_distinct_row_col_filters_quirk():
     """4-tuple wave: the *_col filters act along W and *_row along H."""
     torch.manual_seed(2)
