@@ -282,6 +282,48 @@ int b200w_dtcwt_inv_j2plus_generic(const float* ll, long long ll_plane_stride, i
 int b200w_scat_j1_generic(const float* x, float* z, float* dre_dr, float* dim_dr, int N, int C, int H, int W,
                           const float* h0, int L0, const float* h1, int L1, int mode, float magbias, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * float64 variants.  The reference computes in torch's default dtype (dwt/lowlevel.py:972,
+ * dtcwt/lowlevel.py:67), so double-precision modules work there.  Here double precision runs the
+ * generic tile kernels (and the 1-D row kernels) compiled for `double`: same arguments as the
+ * float32 entry points with `double` in place of `float`, same return codes, same stream semantics.
+ * (The streaming / pyramid fast paths and b200w_dwt_forward are float32-only.)
+ */
+int b200w_dwt_afb2d_f64(const double* x, long long x_plane_stride, int x_pitch,
+                        double* ll, long long ll_plane_stride, int ll_pitch, double* highs,
+                        int planes, int H, int W,
+                        const double* fw_lo, const double* fw_hi, int Lw,
+                        const double* fh_lo, const double* fh_hi, int Lh, int mode, void* stream);
+int b200w_dwt_sfb2d_f64(const double* ll, long long ll_plane_stride, int ll_pitch, const double* highs,
+                        double* y, long long y_plane_stride, int y_pitch,
+                        int planes, int Hc, int Wc, int Ho, int Wo,
+                        const double* gh_lo, const double* gh_hi, int Lh,
+                        const double* gw_lo, const double* gw_hi, int Lw, int mode, void* stream);
+int b200w_dwt_afb1d_f64(const double* x, long long x_pitch, int rows, int N, double* lo, double* hi,
+                        const double* f0, const double* f1, int L, int mode, void* stream);
+int b200w_dwt_sfb1d_f64(const double* lo, const double* hi, int rows, int K, double* y, int Nout,
+                        const double* g0, const double* g1, int L, int mode, void* stream);
+int b200w_dtcwt_fwd_j1_f64(const double* x, long long x_plane_stride, int x_pitch,
+                           double* ll, long long ll_plane_stride, int ll_pitch,
+                           double* highs, const long long hs[6], int N, int C, int H, int W,
+                           const double* h0, int L0, const double* h1, int L1, int mode, void* stream);
+int b200w_dtcwt_fwd_j2plus_f64(const double* x, long long x_plane_stride, int x_pitch,
+                               double* ll, long long ll_plane_stride, int ll_pitch,
+                               double* highs, const long long hs[6], int N, int C, int H, int W,
+                               const double* h0a, const double* h1a, const double* h0b, const double* h1b,
+                               int m, void* stream);
+int b200w_dtcwt_inv_j1_f64(const double* ll, long long ll_plane_stride, int ll_pitch,
+                           const double* highs, const long long hs[6],
+                           double* y, long long y_plane_stride, int y_pitch, int N, int C, int H, int W,
+                           const double* g0, int L0, const double* g1, int L1, int mode, void* stream);
+int b200w_dtcwt_inv_j2plus_f64(const double* ll, long long ll_plane_stride, int ll_pitch,
+                               const double* highs, const long long hs[6],
+                               double* y, long long y_plane_stride, int y_pitch, int N, int C, int H, int W,
+                               const double* g0a, const double* g1a, const double* g0b, const double* g1b,
+                               int m, void* stream);
+int b200w_scat_j1_f64(const double* x, double* z, double* dre_dr, double* dim_dr, int N, int C, int H, int W,
+                      const double* h0, int L0, const double* h1, int L1, int mode, double magbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,10 @@ SYMBOLS = [
     'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1', 'b200w_dwt_forward',
 ]
 KERNEL_ENTRIES = SYMBOLS[5:13]
-SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + [
+# float64: the generic tile kernels and the 1-D row kernels compiled for double (csrc/k_f64.cu)
+F64_ENTRIES = ['b200w_dwt_afb2d', 'b200w_dwt_sfb2d', 'b200w_dwt_afb1d', 'b200w_dwt_sfb1d', 'b200w_dtcwt_fwd_j1',
+               'b200w_dtcwt_fwd_j2plus', 'b200w_dtcwt_inv_j1', 'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1']
+SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + [s + '_f64' for s in F64_ENTRIES] + [
     'b200w_dwt_forward_workspace', 'b200w_dwt_afb1d', 'b200w_dwt_sfb1d', 'b200w_comm_unique_id', 'b200w_comm_init', 'b200w_comm_destroy', 'b200w_allgather',
     'b200w_comm_last_error']
 
@@ -75,6 +78,10 @@ def lib():
         L.b200w_comm_last_error.restype = ctypes.c_char_p
         for s in KERNEL_ENTRIES:
             getattr(L, s + '_generic').argtypes = getattr(L, s).argtypes
+        for s in F64_ENTRIES:
+            if hasattr(L, s + '_f64'):   # (older experimental builds loaded through B200W_LIB lack them)
+                getattr(L, s + '_f64').argtypes = [ctypes.c_double if a is ctypes.c_float else a
+                                                   for a in getattr(L, s).argtypes]
         _lib = L
     return _lib
 
@@ -97,8 +104,11 @@ class generic_kernels(object):
         return False
 
 
-def entry(name):
-    """The C-ABI function for a kernel entry point (honours ``generic_kernels``)."""
+def entry(name, dtype=torch.float32):
+    """The C-ABI function for a kernel entry point (honours ``generic_kernels``); float64 tensors take the ``_f64``
+    entry points (generic tile kernels compiled for double -- the fast paths are float32-only)."""
+    if dtype == torch.float64:
+        return getattr(lib(), name + '_f64')
     return getattr(lib(), name + '_generic' if _USE_GENERIC else name)
 
 
@@ -126,12 +136,18 @@ def check(rc, what):
 # .copy_()) invalidates it, and a new tensor that happens to reuse a freed address can never alias it.
 
 class HostTaps(object):
-    __slots__ = ('arr', 'ptr', 'n')
+    __slots__ = ('arr', 'ptr', 'n', 'arr64', 'ptr64')
 
     def __init__(self, arr):
-        self.arr = np.ascontiguousarray(arr, dtype=np.float32).ravel()
+        self.arr64 = np.ascontiguousarray(arr, dtype=np.float64).ravel()
+        self.ptr64 = self.arr64.ctypes.data_as(ctypes.c_void_p)
+        self.arr = np.ascontiguousarray(self.arr64, dtype=np.float32)
         self.ptr = self.arr.ctypes.data_as(ctypes.c_void_p)
         self.n = int(self.arr.size)
+
+    def p(self, dtype):
+        """Host pointer of the taps in the precision of the tensors of this call."""
+        return self.ptr64 if dtype == torch.float64 else self.ptr
 
 
 def host_taps(t):
@@ -168,14 +184,21 @@ def invalidate_host_taps(obj):
 
 # ---- tensors ------------------------------------------------------------------------------------------
 
-def require_cuda_f32(t, name):
+def require_cuda_real(t, name, like=None):
+    """CUDA float32 (every fast path) or float64 (generic kernels) tensors only; ``like``: dtype it must share."""
     if not isinstance(t, torch.Tensor):
         raise TypeError('%s must be a torch.Tensor' % name)
     if not t.is_cuda:
         raise NotImplementedError(
             '%s is on %s: the b200wave engine runs on CUDA (sm_100a) only and has no CPU fallback' % (name, t.device))
-    if t.dtype != torch.float32:
-        raise NotImplementedError('%s has dtype %s: the b200wave engine computes in float32 only' % (name, t.dtype))
+    if t.dtype not in (torch.float32, torch.float64):
+        raise NotImplementedError('%s has dtype %s: the b200wave engine computes in float32 or float64' % (name, t.dtype))
+    if like is not None and t.dtype != like:
+        raise TypeError('%s has dtype %s, expected %s' % (name, t.dtype, like))   # the reference's conv2d raises too
+    return t.dtype
+
+
+require_cuda_f32 = require_cuda_real   # older name
 
 
 def planes_view(t):

@@ -22,11 +22,19 @@
 #define B200W_FOR_THREADS(tid, NT) { const int tid = (int)threadIdx.x;
 #define B200W_END_THREADS }
 #define B200W_SYNC() __syncthreads()
+#ifdef B200W_F64   /* k_f64.cu compiles the generic kernels once more with the element type redefined to double */
+#define B200W_MUL(a, b) __dmul_rn((a), (b))
+#define B200W_ADD(a, b) __dadd_rn((a), (b))
+#define B200W_SUB(a, b) __dsub_rn((a), (b))
+#define B200W_SQRT(a) __dsqrt_rn(a)
+#define B200W_DIV(a, b) __ddiv_rn((a), (b))
+#else
 #define B200W_MUL(a, b) __fmul_rn((a), (b))
 #define B200W_ADD(a, b) __fadd_rn((a), (b))
 #define B200W_SUB(a, b) __fsub_rn((a), (b))
 #define B200W_SQRT(a) __fsqrt_rn(a)
 #define B200W_DIV(a, b) __fdiv_rn((a), (b))
+#endif
 #else
 #define B200W_FOR_THREADS(tid, NT) for (int tid = 0; tid < (NT); ++tid) {
 #define B200W_END_THREADS }
@@ -41,7 +49,7 @@
 namespace b200w {
 
 constexpr int kMaxTaps = B200W_MAX_TAPS;
-constexpr float kInvSqrt2 = 0.70710678118654752440f;
+constexpr float kInvSqrt2 = (float)0.70710678118654752440;   // (a cast, not a suffix: k_f64.cu redefines the type)
 
 // Filter taps travel as kernel parameters (constant bank): with a compile-time tap index the FFMA
 // takes its coefficient straight from c[0x0][..]; with a runtime index it is one LDC.

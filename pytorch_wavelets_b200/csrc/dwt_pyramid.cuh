@@ -32,13 +32,7 @@ __device__ unsigned long long g_pyr_prof[64];   // [role (0 producer, 1 writer, 
 #define PYR_FLUSH(role, lane) do {} while (0)
 #endif
 
-#ifndef B200W_PYR_SPLIT
-#define B200W_PYR_SPLIT 1
-#endif
-#ifndef B200W_PYR_NSLOT
-#define B200W_PYR_NSLOT 4
-#endif
-constexpr int kPyrSplitC = B200W_PYR_SPLIT, kPyrNSlotC = B200W_PYR_NSLOT;   // the shape the kernel is compiled for (plan_pyramid_best only offers it)
+constexpr int kPyrNSlotC = B200W_PYR_NSLOT;   // the shape the kernel is compiled for (plan_pyramid_best only offers it)
 
 template <int L>
 struct PyrCfg {
@@ -49,6 +43,7 @@ struct PyrCfg {
   static constexpr int HS = pyr_hs(L);      // output rows per stage
   static constexpr int RS = 2 * HS;         // extended input rows per stage
   static constexpr int HALO = pyr_halo(L);
+  static constexpr int SPLIT = pyr_split(L); // staging groups per stage
   static constexpr int NX = 2 * NC + PL;    // floats a lane reads per staged row
   static_assert(HS >= 4 && HS % 2 == 0 && HS % UNR == 0, "stage = whole window periods, even");
 };
@@ -145,7 +140,7 @@ __device__ __forceinline__ void pyr_producer(const PyrParams& p, int plane, floa
 template <int L>
 __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float* smem, unsigned bar0, int lane) {
   using C = PyrCfg<L>;
-  const int SG = C::HS / kPyrSplitC;             // rows per staging group
+  const int SG = C::HS / C::SPLIT;             // rows per staging group
   const int R = kPyrNGO * SG;                    // rows in a staging ring
   // lanes 0..3: the 16-byte aligned middle of one band each; lanes 8..31: one head / tail element of a band each
   const bool bulk_lane = lane < 4;
@@ -159,7 +154,7 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
   for (int l = 0; l < kPyrMaxLevels; ++l) {
     next_g[l] = 0; rslot[l] = 0; gb[l] = nullptr; stb[l] = 0; ph[l] = 0;
     if (l < p.J) {
-      remaining += p.lv[l].n_stage * kPyrSplitC;
+      remaining += p.lv[l].n_stage * C::SPLIT;
       if (myb < p.lv[l].nbands) {
         gb[l] = pyr_band_base(p, l, myb, plane);
         ph[l] = pyr_phase(gb[l]);
@@ -177,7 +172,7 @@ __device__ __forceinline__ void pyr_writer(const PyrParams& p, int plane, float*
       if (l >= p.J) break;
       const PyrLevel& v = p.lv[l];
       const int g = next_g[l];
-      if (g >= v.n_stage * kPyrSplitC) continue;
+      if (g >= v.n_stage * C::SPLIT) continue;
       const int bar = v.bar_out + g % kPyrNGO;
       if (!__all_sync(0xffffffffu, mbar_test(bar0 + 8 * bar, (unsigned)((g / kPyrNGO) & 1)))) continue;
       any = true;
@@ -366,7 +361,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
   PyrEmit<L> em;
   em.capb = 4u * (unsigned)v.st_cap; em.wob = 4u * (unsigned)v.Wo; em.nv = nv; em.nb = v.nbands;
   em.capb3 = 4u * (unsigned)v.st_cap_ll; em.wob3 = 4u * (unsigned)p.ll_pitch;
-  em.kslot = 0; em.R = kPyrNGO * (C::HS / kPyrSplitC);
+  em.kslot = 0; em.R = kPyrNGO * (C::HS / C::SPLIT);
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     em.st_s[b] = smem_s + 4u * (unsigned)(v.st_off + (b < v.nbands ? b : 0) * v.st_cap);
@@ -428,7 +423,7 @@ __device__ __forceinline__ void pyr_worker(const PyrParams& p, int plane, int lv
   int g_seen = 0, g_rel = 0;   // levels >= 1: input groups waited for / released so far
   const int prev_stages = (lvl > 0) ? p.lv[lvl - 1].n_stage : 0;
   const int pitch4 = 4 * v.in_pitch;
-  constexpr int split = kPyrSplitC, nslot = kPyrNSlotC;
+  constexpr int split = C::SPLIT, nslot = kPyrNSlotC;
 
 #pragma unroll 1
   for (int t = 0; t < v.n_stage; ++t) {
@@ -610,7 +605,7 @@ inline int launch_pyramid_v(const PyrParams& p, cudaStream_t stream, int slot) {
 template <int L>
 inline int launch_pyramid(const PyrParams& p, cudaStream_t stream) {
   if (p.planes <= 0) return 0;
-  if (p.threads <= 160) return launch_pyramid_v<L, 160, B200W_PYR_MINB_SMALL>(p, stream, 0);
+  if (p.threads <= 160) return launch_pyramid_v<L, 160, pyr_minb_small(L)>(p, stream, 0);
   if (p.threads <= 256) return launch_pyramid_v<L, 256, 2>(p, stream, 1);
   return launch_pyramid_v<L, 512, 1>(p, stream, 2);
 }

@@ -28,6 +28,14 @@ constexpr int kPyrMaxTaps = 16;
 #endif
 constexpr int kPyrNC = B200W_PYR_NC;      // output columns per lane
 constexpr int kPyrNGO = 2;     // staging groups per level (ring depth)
+// the shared-memory shape the kernel is compiled for (and the only one the plan offers): input-ring slots of half a
+// level-1 stage each, staging groups per worker stage
+#ifndef B200W_PYR_SPLIT
+#define B200W_PYR_SPLIT 2   /* half-stage staging groups: 53 KB per single-level CTA -> 4 CTAs per SM (r02_notes.md) */
+#endif
+#ifndef B200W_PYR_NSLOT
+#define B200W_PYR_NSLOT 4
+#endif
 constexpr int kPyrAuxWarps = 2;  // warp 0 = producer, warp 1 = writer
 
 struct PyrLevel {
@@ -68,6 +76,9 @@ constexpr int pyr_hs(int L) {     // half-stages (= output rows) per stage: a mu
   return (L / 2) * m;
 }
 constexpr int pyr_halo(int L) { return (L - 2 + 3) / 4 * 4; }   // left pad of a ring row (floats)
+// staging groups per worker stage: half-stage groups where a half stage is an even number of rows (its ring then wraps on
+// a 16-byte boundary for every width), whole-stage groups otherwise
+constexpr int pyr_split(int L) { return (pyr_hs(L) % 4 == 0) ? B200W_PYR_SPLIT : 1; }
 
 // ---- group / stage index rules (host plan simulation and device code use the same functions) -----------------
 // rows of group g of a level with Ho output rows: [g*HS - PRO, (g+1)*HS - PRO) clipped to [0, Ho)
@@ -171,32 +182,31 @@ inline int plan_pyramid(PyrParams& p, int planes, int H, int W, int J, int L, in
 }
 
 // CTAs per SM the kernel instantiation for `threads` is compiled for (__launch_bounds__ in dwt_pyramid.cuh)
+// (a 5-warp CTA -- one level of up to 96 lanes -- runs 4 per SM in 96 registers for filters up to 8 taps; longer
+// filters spill under that cap and stay at 3)
 #ifndef B200W_PYR_MINB_SMALL
-#define B200W_PYR_MINB_SMALL 3
+#define B200W_PYR_MINB_SMALL 4
 #endif
-inline int pyr_ctas_for_threads(int threads) { return threads <= 160 ? B200W_PYR_MINB_SMALL : (threads <= 256 ? 2 : 1); }
+constexpr int pyr_minb_small(int L) { return (L <= 8) ? B200W_PYR_MINB_SMALL : (B200W_PYR_MINB_SMALL < 3 ? B200W_PYR_MINB_SMALL : 3); }
+inline int pyr_ctas_for_threads(int threads, int L) { return threads <= 160 ? pyr_minb_small(L) : (threads <= 256 ? 2 : 1); }
 
 // Picks the shared-memory shape that lets the most CTAs share an SM (up to what the register budget of the matching
 // kernel instantiation allows), preferring the deeper rings among equals.
 inline int plan_pyramid_best(PyrParams& p, int planes, int H, int W, int J, int L, int mode, long long xps, int xpitch,
                              const void* x, int max_smem_bytes, int sm_smem_bytes, int ll_pitch = 0) {
-#ifdef B200W_PYR_FORCE_NSLOT   /* experiments: one fixed shape */
-#define B200W_PYR_FS {B200W_PYR_FORCE_NSLOT, B200W_PYR_FORCE_SPLIT, 1}
-  static const int shapes[4][3] = {B200W_PYR_FS, B200W_PYR_FS, B200W_PYR_FS, B200W_PYR_FS};
-#else
-  // (smaller shapes -- 3 input slots, half-stage staging groups, no spare ring group -- fit a third 8-warp CTA per SM,
-  // but the kernel then has to live in 80 registers and spills: measured 2.6x slower, profiles/r02_notes.md)
-  static const int shapes[4][3] = {{4, 1, 1}, {4, 1, 1}, {4, 1, 1}, {4, 1, 1}};
-#endif
+  // 4 input slots, half-stage staging groups.  Measured (profiles/r02_notes.md; level 1 of 4096 x 512^2, db4): whole-stage
+  // groups 1.67 ms at 3 CTAs/SM, 3 slots + half-stage groups 1.59 ms and this shape 1.55 ms at 4 CTAs/SM; an 80-register
+  // 8-warp form that fits a third 3-level CTA spills (2.6x slower).
+  const int shapes[1][3] = {{B200W_PYR_NSLOT, pyr_split(L), 1}};
   PyrParams best;
   int best_ctas = 0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 1; ++i) {
     PyrParams q;
     if (plan_pyramid(q, planes, H, W, J, L, mode, xps, xpitch, x, max_smem_bytes, shapes[i][0], shapes[i][1],
                      shapes[i][2], ll_pitch))
       continue;
     const int by_smem = sm_smem_bytes / (q.smem_bytes + 1024);
-    const int ctas = imin(by_smem, pyr_ctas_for_threads(q.threads));
+    const int ctas = imin(by_smem, pyr_ctas_for_threads(q.threads, L));
     if (ctas > best_ctas) { best_ctas = ctas; best = q; }
   }
   if (best_ctas == 0) return 1;

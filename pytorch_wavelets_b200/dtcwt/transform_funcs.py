@@ -90,7 +90,7 @@ def _is_empty(t):
 
 def fwd_j1(x, h0, h1, skip_hps, o5, ri, mode):
     """ll, highs (None when skipped) for one level-1 transform; o5/ri as returned by get_dimensions5."""
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     L = _ffi.lib()
     h0, h1 = _ffi.host_taps(h0), _ffi.host_taps(h1)
     N, C, H, W = x.shape
@@ -105,15 +105,15 @@ def fwd_j1(x, h0, h1, skip_hps, o5, ri, mode):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j1 %dx%d' % (H, W),
                                                     4 * N * C * H * W * (2 if skip_hps else 5)):
-            rc = _ffi.entry('b200w_dtcwt_fwd_j1')(x.data_ptr(), xps, xpitch, ll.data_ptr(), H * W, W,
+            rc = _ffi.entry('b200w_dtcwt_fwd_j1', dt)(x.data_ptr(), xps, xpitch, ll.data_ptr(), H * W, W,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
-                                      N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n, mode, _ffi.stream_of(x))
+                                      N, C, H, W, h0.p(dt), h0.n, h1.p(dt), h1.n, mode, _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dtcwt_fwd_j1')
     return ll, highs
 
 
 def fwd_j2plus(x, h0a, h1a, h0b, h1b, skip_hps, o5, ri):
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     L = _ffi.lib()
     N, C, H, W = x.shape
     if H % 4 != 0:
@@ -130,9 +130,9 @@ def fwd_j2plus(x, h0a, h1a, h0b, h1b, skip_hps, o5, ri):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dtcwt_fwd_j2plus %dx%d' % (H, W),
                                                     N * C * H * W * (5 if skip_hps else 8)):
-            rc = _ffi.entry('b200w_dtcwt_fwd_j2plus')(x.data_ptr(), xps, xpitch, ll.data_ptr(), (H // 2) * (W // 2), W // 2,
+            rc = _ffi.entry('b200w_dtcwt_fwd_j2plus', dt)(x.data_ptr(), xps, xpitch, ll.data_ptr(), (H // 2) * (W // 2), W // 2,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
-                                          N, C, H, W, f[0].ptr, f[1].ptr, f[2].ptr, f[3].ptr, f[0].n,
+                                          N, C, H, W, f[0].p(dt), f[1].p(dt), f[2].p(dt), f[3].p(dt), f[0].n,
                                           _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dtcwt_fwd_j2plus')
     return ll, highs
@@ -146,19 +146,20 @@ def _inv_prepare(ll, highs, o5, ri, what):
     if ll is None and highs is None:
         raise ValueError('%s needs a low-pass or a band-pass input' % what)
     sz = None
+    dt = None
     if highs is not None:
-        _ffi.require_cuda_f32(highs, 'highs')
+        dt = _ffi.require_cuda_real(highs, 'highs')
         highs = highs.contiguous()
         sz = _highs_dims(highs, o5, ri)
     if ll is not None:
-        _ffi.require_cuda_f32(ll, 'lows')
-    return ll, highs, sz
+        dt = _ffi.require_cuda_real(ll, 'lows', dt)
+    return ll, highs, sz, dt
 
 
 def inv_j1(ll, highs, g0, g1, o5, ri, mode):
     """Level-1 synthesis.  ``ll`` (N,C,H,W) or None, ``highs`` 6-D or None."""
     L = _ffi.lib()
-    ll, highs, sz = _inv_prepare(ll, highs, o5, ri, 'inv_j1')
+    ll, highs, sz, dt = _inv_prepare(ll, highs, o5, ri, 'inv_j1')
     g0, g1 = _ffi.host_taps(g0), _ffi.host_taps(g1)
     hs = [0] * 6
     if highs is not None:
@@ -191,9 +192,9 @@ def inv_j1(ll, highs, g0, g1, o5, ri, mode):
     if N * C > 0:
         with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j1 %dx%d' % (H, W),
                                                       4 * N * C * H * W * (1 + (ll is not None) + 3 * (highs is not None))):
-            rc = _ffi.entry('b200w_dtcwt_inv_j1')(None if ll is None else ll.data_ptr(), llps, llpitch,
+            rc = _ffi.entry('b200w_dtcwt_inv_j1', dt)(None if ll is None else ll.data_ptr(), llps, llpitch,
                                       None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
-                                      y.data_ptr(), H * W, W, N, C, H, W, g0.ptr, g0.n, g1.ptr, g1.n, mode,
+                                      y.data_ptr(), H * W, W, N, C, H, W, g0.p(dt), g0.n, g1.p(dt), g1.n, mode,
                                       _ffi.stream_of(ref))
         _ffi.check(rc, 'b200w_dtcwt_inv_j1')
     return y
@@ -202,7 +203,7 @@ def inv_j1(ll, highs, g0, g1, o5, ri, mode):
 def inv_j2plus(ll, highs, g0a, g1a, g0b, g1b, o5, ri):
     """Level>=2 synthesis: ``ll`` (N,C,H,W) or None, ``highs`` at (H/2,W/2) or None -> (N,C,2H,2W)."""
     L = _ffi.lib()
-    ll, highs, sz = _inv_prepare(ll, highs, o5, ri, 'inv_j2plus')
+    ll, highs, sz, dt = _inv_prepare(ll, highs, o5, ri, 'inv_j2plus')
     f = [_ffi.host_taps(t) for t in (g0a, g1a, g0b, g1b)]
     hs = [0] * 6
     if ll is not None:
@@ -225,10 +226,10 @@ def inv_j2plus(ll, highs, g0a, g1a, g0b, g1b, o5, ri):
     if N * C > 0:
         with torch.cuda.device(ref.device), _ffi.span('dtcwt_inv_j2plus %dx%d' % (H, W),
                                                       4 * N * C * H * W * (4 + (ll is not None) + 3 * (highs is not None))):
-            rc = _ffi.entry('b200w_dtcwt_inv_j2plus')(None if ll is None else ll.data_ptr(), llps, llpitch,
+            rc = _ffi.entry('b200w_dtcwt_inv_j2plus', dt)(None if ll is None else ll.data_ptr(), llps, llpitch,
                                           None if highs is None else highs.data_ptr(), _ffi.hs_array(hs),
                                           y.data_ptr(), 4 * H * W, 2 * W, N, C, H, W,
-                                          f[0].ptr, f[1].ptr, f[2].ptr, f[3].ptr, f[0].n, _ffi.stream_of(ref))
+                                          f[0].p(dt), f[1].p(dt), f[2].p(dt), f[3].p(dt), f[0].n, _ffi.stream_of(ref))
         _ffi.check(rc, 'b200w_dtcwt_inv_j2plus')
     return y
 

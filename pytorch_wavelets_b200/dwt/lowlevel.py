@@ -98,7 +98,7 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     Returns (ll (N,C,Ho,Wo), highs (N,C,3,Ho,Wo)); highs is contiguous, ll is contiguous unless ``pad_ll``:
     then its row pitch is rounded up to a 128-byte line (an internal hand-off between levels: this level
     writes it, and the next level stages it, as whole aligned lines)."""
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     _check_bank_mode(mode)
     if x.dim() != 4:
         raise ValueError('expected a 4-D (N,C,H,W) input, got shape {}'.format(tuple(x.shape)))
@@ -117,9 +117,9 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
     highs = x.new_empty((N, C, 3, Ho, Wo))
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dwt_afb2d %dx%d L%d' % (H, W, fw_lo.n),
-                                                    4 * N * C * (H * W + 4 * Ho * Wo)):
-            rc = _ffi.entry('b200w_dwt_afb2d')(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wp, Wp, highs.data_ptr(),
-                                   N * C, H, W, fw_lo.ptr, fw_hi.ptr, fw_lo.n, fh_lo.ptr, fh_hi.ptr, fh_lo.n,
+                                                    x.element_size() * N * C * (H * W + 4 * Ho * Wo)):
+            rc = _ffi.entry('b200w_dwt_afb2d', dt)(x.data_ptr(), xps, xpitch, ll.data_ptr(), Ho * Wp, Wp, highs.data_ptr(),
+                                   N * C, H, W, fw_lo.p(dt), fw_hi.p(dt), fw_lo.n, fh_lo.p(dt), fh_hi.p(dt), fh_lo.n,
                                    mode, _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dwt_afb2d')
     return ll, highs
@@ -128,13 +128,13 @@ def afb2d_level(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, pad_ll=False):
 def sfb2d_level(ll, highs, gh_lo, gh_hi, gw_lo, gw_hi, mode, out_hw=None):
     """One synthesis level on the GPU.  ``gh_*`` act along H (first pass), ``gw_*`` along W.
     ``highs`` may be None (zeros).  ``out_hw`` crops the output (AFB2D.backward)."""
-    _ffi.require_cuda_f32(ll, 'low')
+    dt = _ffi.require_cuda_real(ll, 'low')
     _check_bank_mode(mode)
     L = _ffi.lib()
     gh_lo, gh_hi, gw_lo, gw_hi = [_ffi.host_taps(f) for f in (gh_lo, gh_hi, gw_lo, gw_hi)]
     N, C, Hc, Wc = ll.shape
     if highs is not None:
-        _ffi.require_cuda_f32(highs, 'highs')
+        _ffi.require_cuda_real(highs, 'highs', dt)
         if tuple(highs.shape) != (N, C, 3, Hc, Wc):
             raise ValueError('highs shape {} does not match low shape {}'.format(tuple(highs.shape), tuple(ll.shape)))
         highs = highs.contiguous()
@@ -148,10 +148,10 @@ def sfb2d_level(ll, highs, gh_lo, gh_hi, gw_lo, gw_hi, mode, out_hw=None):
     y = ll.new_empty((N, C, Ho, Wo))
     if N * C > 0:
         with torch.cuda.device(ll.device), _ffi.span('dwt_sfb2d %dx%d L%d' % (Hc, Wc, gh_lo.n),
-                                                     4 * N * C * ((1 if highs is None else 4) * Hc * Wc + Ho * Wo)):
-            rc = _ffi.entry('b200w_dwt_sfb2d')(ll.data_ptr(), llps, llpitch, None if highs is None else highs.data_ptr(),
+                                                     ll.element_size() * N * C * ((1 if highs is None else 4) * Hc * Wc + Ho * Wo)):
+            rc = _ffi.entry('b200w_dwt_sfb2d', dt)(ll.data_ptr(), llps, llpitch, None if highs is None else highs.data_ptr(),
                                    y.data_ptr(), Ho * Wo, Wo, N * C, Hc, Wc, Ho, Wo,
-                                   gh_lo.ptr, gh_hi.ptr, gh_lo.n, gw_lo.ptr, gw_hi.ptr, gw_lo.n, mode,
+                                   gh_lo.p(dt), gh_hi.p(dt), gh_lo.n, gw_lo.p(dt), gw_hi.p(dt), gw_lo.n, mode,
                                    _ffi.stream_of(ll))
         _ffi.check(rc, 'b200w_dwt_sfb2d')
     return y
@@ -161,7 +161,7 @@ def dwt_forward_levels(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, J):
     """All J analysis levels through ONE C-ABI call (``b200w_dwt_forward``): a single fused kernel launch when the
     pyramid kernel applies (no inter-level low-pass in device memory), one launch per level otherwise.
     Returns ``(yl (N,C,H_J,W_J), [yh_1 .. yh_J])`` -- contiguous, the reference's return layout."""
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     _check_bank_mode(mode)
     if x.dim() != 4:
         raise ValueError('expected a 4-D (N,C,H,W) input, got shape {}'.format(tuple(x.shape)))
@@ -169,6 +169,12 @@ def dwt_forward_levels(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, J):
     fw_lo, fw_hi, fh_lo, fh_hi = [_ffi.host_taps(f) for f in (fw_lo, fw_hi, fh_lo, fh_hi)]
     if fw_lo.n != fw_hi.n or fh_lo.n != fh_hi.n:
         raise ValueError('low-pass and high-pass filters must have equal length')
+    if dt == torch.float64:   # double precision: one generic-kernel launch per level (b200w_dwt_forward is float32-only)
+        ll, yh = x, []
+        for _ in range(J):
+            ll, h = afb2d_level(ll, fw_lo, fw_hi, fh_lo, fh_hi, mode)
+            yh.append(h)
+        return ll, yh
     N, C, H, W = x.shape
     x, xps, xpitch = _ffi.planes_view(x)
     sizes = []
@@ -189,7 +195,7 @@ def dwt_forward_levels(x, fw_lo, fw_hi, fh_lo, fh_hi, mode, J):
             tag = ('dwt_pyramid' if wsb == 0 else 'dwt_levels') + ' %dx%d L%d J%d' % (H, W, fw_lo.n, J)
             with _ffi.span(tag, alg):
                 rc = _ffi.entry('b200w_dwt_forward')(x.data_ptr(), xps, xpitch, N * C, H, W, J, yl.data_ptr(), ptrs,
-                                                     fw_lo.ptr, fw_hi.ptr, fw_lo.n, fh_lo.ptr, fh_hi.ptr, fh_lo.n,
+                                                     fw_lo.p(dt), fw_hi.p(dt), fw_lo.n, fh_lo.p(dt), fh_hi.p(dt), fh_lo.n,
                                                      mode, None if ws is None else ws.data_ptr(), wsb,
                                                      _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dwt_forward')

@@ -11,7 +11,7 @@ from pytorch_wavelets_b200.dwt import lowlevel
 
 def afb1d_level(x, h0, h1, mode):
     """x (N, C, L) -> lo, hi (N, C, K); stored (reversed) analysis taps."""
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     lowlevel._check_bank_mode(mode)
     L = _ffi.lib()
     h0, h1 = _ffi.host_taps(h0), _ffi.host_taps(h1)
@@ -23,7 +23,7 @@ def afb1d_level(x, h0, h1, mode):
     lo, hi = x.new_empty((N, C, K)), x.new_empty((N, C, K))
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('dwt_afb1d %d L%d' % (n, h0.n), 4 * N * C * (n + 2 * K)):
-            rc = L.b200w_dwt_afb1d(x.data_ptr(), n, N * C, n, lo.data_ptr(), hi.data_ptr(), h0.ptr, h1.ptr, h0.n, mode,
+            rc = (L.b200w_dwt_afb1d_f64 if dt == torch.float64 else L.b200w_dwt_afb1d)(x.data_ptr(), n, N * C, n, lo.data_ptr(), hi.data_ptr(), h0.p(dt), h1.p(dt), h0.n, mode,
                                    _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_dwt_afb1d')
     return lo, hi
@@ -31,14 +31,14 @@ def afb1d_level(x, h0, h1, mode):
 
 def sfb1d_level(lo, hi, g0, g1, mode, out_len=None):
     """lo, hi (N, C, K) (hi may be None) -> y (N, C, rec_len) or cropped to ``out_len``; stored synthesis taps."""
-    _ffi.require_cuda_f32(lo, 'low')
+    dt = _ffi.require_cuda_real(lo, 'low')
     lowlevel._check_bank_mode(mode)
     L = _ffi.lib()
     g0, g1 = _ffi.host_taps(g0), _ffi.host_taps(g1)
     lo = lo.contiguous()
     N, C, K = lo.shape
     if hi is not None:
-        _ffi.require_cuda_f32(hi, 'high')
+        _ffi.require_cuda_real(hi, 'high', dt)
         if tuple(hi.shape) != tuple(lo.shape):
             raise ValueError('high shape {} does not match low shape {}'.format(tuple(hi.shape), tuple(lo.shape)))
         hi = hi.contiguous()
@@ -50,8 +50,8 @@ def sfb1d_level(lo, hi, g0, g1, mode, out_len=None):
     y = lo.new_empty((N, C, n))
     if N * C > 0:
         with torch.cuda.device(lo.device), _ffi.span('dwt_sfb1d %d L%d' % (K, g0.n), 4 * N * C * (2 * K + n)):
-            rc = L.b200w_dwt_sfb1d(lo.data_ptr(), None if hi is None else hi.data_ptr(), N * C, K, y.data_ptr(), n,
-                                   g0.ptr, g1.ptr, g0.n, mode, _ffi.stream_of(lo))
+            rc = (L.b200w_dwt_sfb1d_f64 if dt == torch.float64 else L.b200w_dwt_sfb1d)(lo.data_ptr(), None if hi is None else hi.data_ptr(), N * C, K, y.data_ptr(), n,
+                                   g0.p(dt), g1.p(dt), g0.n, mode, _ffi.stream_of(lo))
         _ffi.check(rc, 'b200w_dwt_sfb1d')
     return y
 

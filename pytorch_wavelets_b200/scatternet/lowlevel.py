@@ -13,7 +13,7 @@ from pytorch_wavelets_b200.dwt.lowlevel import int_to_mode, mode_to_int  # noqa:
 
 def scat_j1(x, h0o, h1o, mode, bias, want_aux):
     """z (N,7,C,H/2,W/2) [, re/r, im/r (N,6,C,H/2,W/2)] from x (N,C,H,W), H and W even."""
-    _ffi.require_cuda_f32(x, 'x')
+    dt = _ffi.require_cuda_real(x, 'x')
     L = _ffi.lib()
     h0, h1 = _ffi.host_taps(h0o), _ffi.host_taps(h1o)
     x = x.contiguous()
@@ -26,8 +26,8 @@ def scat_j1(x, h0o, h1o, mode, bias, want_aux):
     if N * C > 0:
         with torch.cuda.device(x.device), _ffi.span('scat_j1 %dx%d' % (H, W),
                                                     N * C * H * W * (4 + 7 + (12 if want_aux else 0))):
-            rc = _ffi.entry('b200w_scat_j1')(x.data_ptr(), z.data_ptr(), None if dre is None else dre.data_ptr(),
-                                 None if dim is None else dim.data_ptr(), N, C, H, W, h0.ptr, h0.n, h1.ptr, h1.n,
+            rc = _ffi.entry('b200w_scat_j1', dt)(x.data_ptr(), z.data_ptr(), None if dre is None else dre.data_ptr(),
+                                 None if dim is None else dim.data_ptr(), N, C, H, W, h0.p(dt), h0.n, h1.p(dt), h1.n,
                                  mode, float(bias), _ffi.stream_of(x))
         _ffi.check(rc, 'b200w_scat_j1')
     return z, dre, dim
