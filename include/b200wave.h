@@ -324,6 +324,31 @@ int b200w_dtcwt_inv_j2plus_f64(const double* ll, long long ll_plane_stride, int 
 int b200w_scat_j1_f64(const double* x, double* z, double* dre_dr, double* dim_dr, int N, int C, int H, int W,
                       const double* h0, int L0, const double* h1, int L1, int mode, double magbias, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Standalone 1-D DTCWT primitives (the reference's low-level API; in the transforms these passes are
+ * fused inside the per-level kernels).  x: (planes, H, W) contiguous; y: contiguous output.
+ *   b200w_dtcwt_filter  = colfilter (along_w = 0) / rowfilter (along_w = 1), reference
+ *                         dtcwt/lowlevel.py:70-94: y[n] = sum_j h[j] x[ext(n + j - L/2)], ext = symmetric
+ *                         or zero padding; ANY length L -- an even L yields N + 1 outputs along the
+ *                         filtered dimension (the reference's behaviour, tests/test_colfilter.py:52-61).
+ *   b200w_dtcwt_dfilt   = coldfilt / rowdfilt (:97-151): (ha, hb) even length m, filtered size % 4 == 0,
+ *                         output half size.
+ *   b200w_dtcwt_ifilt   = colifilt / rowifilt (:154-239): filtered size % 2 == 0, output double size.
+ * Taps are host pointers in stored (reversed) order, as everywhere in this ABI.
+ */
+int b200w_dtcwt_filter(const float* x, float* y, int planes, int H, int W, const float* h, int L,
+                       int symmetric, int along_w, void* stream);
+int b200w_dtcwt_dfilt(const float* x, float* y, int planes, int H, int W, const float* ha, const float* hb,
+                      int m, int highpass, int along_w, void* stream);
+int b200w_dtcwt_ifilt(const float* x, float* y, int planes, int H, int W, const float* ha, const float* hb,
+                      int m, int highpass, int along_w, void* stream);
+int b200w_dtcwt_filter_f64(const double* x, double* y, int planes, int H, int W, const double* h, int L,
+                           int symmetric, int along_w, void* stream);
+int b200w_dtcwt_dfilt_f64(const double* x, double* y, int planes, int H, int W, const double* ha,
+                          const double* hb, int m, int highpass, int along_w, void* stream);
+int b200w_dtcwt_ifilt_f64(const double* x, double* y, int planes, int H, int W, const double* ha,
+                          const double* hb, int m, int highpass, int along_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

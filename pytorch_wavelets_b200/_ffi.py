@@ -31,7 +31,9 @@ F64_ENTRIES = ['b200w_dwt_afb2d', 'b200w_dwt_sfb2d', 'b200w_dwt_afb1d', 'b200w_d
                'b200w_dtcwt_fwd_j2plus', 'b200w_dtcwt_inv_j1', 'b200w_dtcwt_inv_j2plus', 'b200w_scat_j1']
 SYMBOLS = SYMBOLS + [s + '_generic' for s in KERNEL_ENTRIES] + [s + '_f64' for s in F64_ENTRIES] + [
     'b200w_dwt_forward_workspace', 'b200w_dwt_afb1d', 'b200w_dwt_sfb1d', 'b200w_comm_unique_id', 'b200w_comm_init', 'b200w_comm_destroy', 'b200w_allgather',
-    'b200w_comm_last_error']
+    'b200w_comm_last_error',
+    'b200w_dtcwt_filter', 'b200w_dtcwt_dfilt', 'b200w_dtcwt_ifilt', 'b200w_dtcwt_filter_f64', 'b200w_dtcwt_dfilt_f64',
+    'b200w_dtcwt_ifilt_f64']
 
 
 class B200WaveError(RuntimeError):
@@ -76,6 +78,11 @@ def lib():
         L.b200w_comm_destroy.argtypes = [c_vp]
         L.b200w_allgather.argtypes = [c_vp, c_vp, c_vp, c_ll, c_vp]
         L.b200w_comm_last_error.restype = ctypes.c_char_p
+        if hasattr(L, 'b200w_dtcwt_filter'):
+            for sfx in ('', '_f64'):
+                getattr(L, 'b200w_dtcwt_filter' + sfx).argtypes = [c_vp, c_vp, c_int, c_int, c_int, pf, c_int, c_int, c_int, c_vp]
+                getattr(L, 'b200w_dtcwt_dfilt' + sfx).argtypes = [c_vp, c_vp, c_int, c_int, c_int, pf, pf, c_int, c_int, c_int, c_vp]
+                getattr(L, 'b200w_dtcwt_ifilt' + sfx).argtypes = [c_vp, c_vp, c_int, c_int, c_int, pf, pf, c_int, c_int, c_int, c_vp]
         for s in KERNEL_ENTRIES:
             getattr(L, s + '_generic').argtypes = getattr(L, s).argtypes
         for s in F64_ENTRIES:

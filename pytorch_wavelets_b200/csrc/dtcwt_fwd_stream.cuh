@@ -25,6 +25,24 @@ __device__ __forceinline__ void q2c_emit(float a, float b, float c, float d, flo
   store_cplx(hq, so, sr, vec, o2, __fadd_rn(a, d), __fsub_rn(b, c));
 }
 
+// sqrt of a non-negative finite sum of squares, branch-free: MUFU.RSQ plus one Newton step on the residual (an exact FMA),
+// with tiny / zero arguments rescaled by selects.  The IEEE routine (__fsqrt_rn) carries a range-check branch and a slow-path
+// call per use; twelve of them per stage serialise twelve dependent MUFU chains, which is what bounded the ScatLayer
+// kernel (profiles/r02_notes.md).  The result is the correctly rounded root except for rare 1-ulp ties -- far inside the
+// 1e-5 parity tolerance against the reference's torch.sqrt.
+__device__ __forceinline__ float sqrt_nonneg(float s) {
+  const bool tiny = s < 1e-30f;
+  const float t = tiny ? s * 18446744073709551616.f : s;          // x 2^64 (exact)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+  float g = t * y;
+  const float h = 0.5f * y;
+  const float e = fmaf(-g, g, t);
+  g = fmaf(e, h, g);
+  g = tiny ? g * 2.3283064365386963e-10f : g;                     // x 2^-32
+  return (s <= 0.f) ? 0.f : g;   // (NaN propagates)
+}
+
 // ScatLayer epilogue for one subband quad: smoothed magnitudes of w1 / w2 (+ re/r, im/r when DERIV: the tensors the
 // backward pass needs -- a separate instantiation, so the inference kernel carries no division code)
 template <bool DERIV>
@@ -38,7 +56,7 @@ __device__ __forceinline__ void scat_emit(float a, float b, float c, float d, co
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const float rr = __fmul_rn(re[k], re[k]), ii = __fmul_rn(im[k], im[k]);
-    const float r = __fsqrt_rn(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
+    const float r = sqrt_nonneg(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
     __stcs(p.z + zbase + (1 + os[k]) * ostride, __fsub_rn(r, p.magbias));
     if (DERIV) {
       __stcs(p.dre + dbase + os[k] * ostride, __fdiv_rn(re[k], r));

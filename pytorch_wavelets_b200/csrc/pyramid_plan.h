@@ -194,17 +194,17 @@ inline int pyr_ctas_for_threads(int threads, int L) { return threads <= 160 ? py
 // kernel instantiation allows), preferring the deeper rings among equals.
 inline int plan_pyramid_best(PyrParams& p, int planes, int H, int W, int J, int L, int mode, long long xps, int xpitch,
                              const void* x, int max_smem_bytes, int sm_smem_bytes, int ll_pitch = 0) {
-  // 4 input slots, half-stage staging groups.  Measured (profiles/r02_notes.md; level 1 of 4096 x 512^2, db4): whole-stage
-  // groups 1.67 ms at 3 CTAs/SM, 3 slots + half-stage groups 1.59 ms and this shape 1.55 ms at 4 CTAs/SM; an 80-register
-  // 8-warp form that fits a third 3-level CTA spills (2.6x slower).
-  const int shapes[1][3] = {{B200W_PYR_NSLOT, pyr_split(L), 1}};
+  // 4 input slots; half-stage staging groups for the single-level CTA (<= 160 threads), whole-stage groups otherwise.
+  // Measured (profiles/r02_notes.md; level 1 of 4096 x 512^2, db4): whole-stage groups 1.67 ms at 3 CTAs/SM, 3 slots +
+  // half-stage groups 1.59 ms, 4 slots + half-stage groups 1.55 ms at 4 CTAs/SM; the 512-thread 3-level CTA is slower with
+  // half-stage groups (0.89 vs 0.70 ms per 268 Mpix at 1024^2); an 80-register 8-warp form for a third 3-level CTA spills.
   PyrParams best;
   int best_ctas = 0;
-  for (int i = 0; i < 1; ++i) {
+  for (int split = 1; split <= 2; ++split) {
     PyrParams q;
-    if (plan_pyramid(q, planes, H, W, J, L, mode, xps, xpitch, x, max_smem_bytes, shapes[i][0], shapes[i][1],
-                     shapes[i][2], ll_pitch))
+    if (plan_pyramid(q, planes, H, W, J, L, mode, xps, xpitch, x, max_smem_bytes, B200W_PYR_NSLOT, split, 1, ll_pitch))
       continue;
+    if (split != ((q.threads <= 160) ? pyr_split(L) : 1)) continue;   // the shape each kernel instantiation is compiled for
     const int by_smem = sm_smem_bytes / (q.smem_bytes + 1024);
     const int ctas = imin(by_smem, pyr_ctas_for_threads(q.threads, L));
     if (ctas > best_ctas) { best_ctas = ctas; best = q; }

@@ -122,6 +122,39 @@ def dwt1d_case(name, shape, J, wave, mode, seed):
     save(name, **d)
 
 
+def prims_case(name, seed):
+    """The reference's standalone 1-D primitives (dtcwt/lowlevel.py:70-239): odd AND even level-1 filter lengths (an even
+    length gives N + 1 outputs, tests/test_colfilter.py:52-61), both extension modes, both q-shift phase-table parities
+    (qshift_a: m/2 = 5 odd, qshift_b: m/2 = 7 odd, qshift_06: m/2 = 5, qshift_c: m/2 = 8 even), low- and high-pass."""
+    from pytorch_wavelets.dtcwt import lowlevel as ll
+    from pytorch_wavelets.dtcwt.coeffs import biort as _biort, qshift as _qshift
+    torch.manual_seed(seed)
+    x = torch.randn(2, 3, 24, 28)
+    d = dict(x=x)
+    rng = np.random.RandomState(seed)
+    for L in (5, 7, 4, 6, 2):
+        h = rng.randn(L)
+        hp = ll.prep_filt(h, 1)
+        d['filt%d_h' % L] = hp.numpy().ravel()
+        for mode in ('symmetric', 'zero'):
+            d['filt%d_col_%s' % (L, mode)] = ll.colfilter(x, hp, mode=mode)
+            d['filt%d_row_%s' % (L, mode)] = ll.rowfilter(x, hp, mode=mode)
+    for q in ('qshift_a', 'qshift_b', 'qshift_c'):
+        h0a, h0b, g0a, g0b, h1a, h1b, g1a, g1b = _qshift(q)
+        ha, hb = ll.prep_filt(h0a, 1), ll.prep_filt(h0b, 1)
+        d['%s_ha' % q] = ha.numpy().ravel(); d['%s_hb' % q] = hb.numpy().ravel()
+        for hp_ in (False, True):
+            d['%s_coldfilt_%d' % (q, hp_)] = ll.coldfilt(x, ha, hb, highpass=hp_)
+            d['%s_rowdfilt_%d' % (q, hp_)] = ll.rowdfilt(x, ha, hb, highpass=hp_)
+            d['%s_colifilt_%d' % (q, hp_)] = ll.colifilt(x, ha, hb, highpass=hp_)
+            d['%s_rowifilt_%d' % (q, hp_)] = ll.rowifilt(x, ha, hb, highpass=hp_)
+    save(name, **d)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'prims':
+    prims_case('prims_24x28', 95)
+    sys.exit(0)
+
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'extra':
     dtcwt_case('dtcwt_b_32_J3_96x64', (1, 1, 96, 64), 3, 'near_sym_b', 'qshift_32', 2, -1, 'symmetric', 90)
     sys.exit(0)

@@ -18,13 +18,27 @@ def _n(t):
     return t.detach().cpu().numpy()
 
 
+class f64_default(object):
+    """Build modules the way the reference's double-precision tests do: with torch's default dtype set to float64, so the
+    filter buffers hold double-precision taps (``.double()`` on a float32 module would keep float32-rounded taps)."""
+
+    def __enter__(self):
+        self.prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+
+    def __exit__(self, *exc):
+        torch.set_default_dtype(self.prev)
+        return False
+
+
 @pytest.mark.parametrize('mode', ['zero', 'symmetric', 'reflect', 'periodic', 'periodization'])
 @pytest.mark.parametrize('wave,J,shape', [('db4', 3, (2, 3, 128, 96)), ('db2', 2, (1, 2, 63, 50)), ('bior2.4', 2, (1, 2, 80, 72))])
 def test_dwt_f64_vs_oracle(wave, J, shape, mode):
     torch.manual_seed(5)
     x = torch.randn(*shape, dtype=torch.float64)
-    f = pw.DWTForward(J=J, wave=wave, mode=mode).double()
-    i = pw.DWTInverse(wave=wave, mode=mode).double()
+    with f64_default():
+        f = pw.DWTForward(J=J, wave=wave, mode=mode)
+        i = pw.DWTInverse(wave=wave, mode=mode)
     assert f.h0_col.dtype == torch.float64
     hf = [b.numpy() for b in (f.h0_col, f.h1_col, f.h0_row, f.h1_row)]
     gf = [b.numpy() for b in (i.g0_col, i.g1_col, i.g0_row, i.g1_row)]
@@ -47,8 +61,9 @@ def test_dwt_f64_vs_oracle(wave, J, shape, mode):
 def test_dtcwt_f64_roundtrip_and_f32_agreement(biort, qshift, shape):
     torch.manual_seed(6)
     x = torch.randn(*shape, dtype=torch.float64, device=DEV)
-    f64 = pw.DTCWTForward(J=3, biort=biort, qshift=qshift).double().to(DEV)
-    i64 = pw.DTCWTInverse(biort=biort, qshift=qshift).double().to(DEV)
+    with f64_default():
+        f64 = pw.DTCWTForward(J=3, biort=biort, qshift=qshift).to(DEV)
+        i64 = pw.DTCWTInverse(biort=biort, qshift=qshift).to(DEV)
     yl, yh = f64(x)
     assert yl.dtype == torch.float64 and all(h.dtype == torch.float64 for h in yh)
     y = i64((yl, yh))
@@ -65,7 +80,8 @@ def test_dtcwt_f64_roundtrip_and_f32_agreement(biort, qshift, shape):
 def test_dtcwt_f64_vs_oracle():
     torch.manual_seed(7)
     x = torch.randn(1, 2, 48, 64, dtype=torch.float64)
-    f = pw.DTCWTForward(J=2).double()
+    with f64_default():
+        f = pw.DTCWTForward(J=2)
     lv1 = [b.numpy().ravel() for b in (f.h0o, f.h1o)]
     qs = [b.numpy().ravel() for b in (f.h0a, f.h0b, f.h1a, f.h1b)]   # the oracle's order
     oyl, oyh = orc.dtcwt_forward(x.numpy(), lv1, qs, J=2)
@@ -78,8 +94,9 @@ def test_dtcwt_f64_vs_oracle():
 def test_dwt1d_and_scat_f64():
     torch.manual_seed(8)
     x = torch.randn(2, 3, 257, dtype=torch.float64, device=DEV)
-    f = pw.DWT1DForward(J=3, wave='db4', mode='symmetric').double().to(DEV)
-    i = pw.DWT1DInverse(wave='db4', mode='symmetric').double().to(DEV)
+    with f64_default():
+        f = pw.DWT1DForward(J=3, wave='db4', mode='symmetric').to(DEV)
+        i = pw.DWT1DInverse(wave='db4', mode='symmetric').to(DEV)
     yl, yh = f(x)
     assert yl.dtype == torch.float64
     y = i((yl, yh))
