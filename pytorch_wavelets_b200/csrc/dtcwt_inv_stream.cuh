@@ -349,6 +349,9 @@ inline int launch_i1_stream(const DtParams& p, cudaStream_t stream) {
   return 0;
 }
 
+// (a 128-column form -- two complex columns per lane, band rows interleaved by filter so that the pass along W is packed
+// FFMA2 as well: -40 % shared-memory wavefronts, -30 % instructions -- was built and measured in round 2: 164-205
+// registers leave 9-12 warps per SM instead of 20, and the level is 10-13 % slower; profiles/r02_notes.md)
 int try_launch_inv_j1(const DtParams& p, cudaStream_t stream) {
   if ((long long)p.N * p.C == 0) return 0;
   if (p.L0 == 7 && p.L1 == 5) return launch_i1_stream<7, 5>(p, stream);   // near_sym_a synthesis

@@ -598,6 +598,83 @@ def test_periodization_inverse_streaming_matches_generic_and_oracle(wave, shape)
     util.assert_close(_n(yb), oy, TOL, 'vs oracle')
 
 
+@pytest.mark.parametrize('mode', ['symmetric', 'zero'])
+def test_wide_dtcwt_level1_inverse_matches_generic_and_oracle(mode):
+    """DTCWT level-1 synthesis on planes several strips wide: widths around the strip boundaries, both extension modes, a
+    missing low-pass / band-pass input, and the backward pass of FWD_J1 (the (5,7) instantiation) -- streaming kernel
+    against the generic tile kernel (same arithmetic: 1e-6) and the oracle."""
+    torch.manual_seed(47)
+    i = pw.DTCWTInverse(biort='near_sym_a', qshift='qshift_a', mode=mode).to(DEV)
+    f = pw.DTCWTForward(J=1, biort='near_sym_a', qshift='qshift_a', mode=mode).to(DEV)
+    g0o, g1o = _n(i.g0o), _n(i.g1o)
+    for k, W in enumerate([128, 132, 136, 192, 252, 256, 260, 388]):
+        H = [16, 18, 30, 44][k % 4]
+        yl = torch.randn(2, 2, H, W, device=DEV)
+        yh = [torch.randn(2, 2, 6, H // 2, W // 2, 2, device=DEV)]
+        with _ffi.generic_kernels():
+            ya = i((yl, yh))
+        yb = i((yl, yh))
+        assert ya.shape == yb.shape == (2, 2, H, W)
+        assert (ya - yb).abs().max().item() <= 1e-6 * max(1.0, ya.abs().max().item()), W
+        util.assert_close(_n(yb), orc.dtcwt_inv_j1(_n(yl), _n(yh[0]), g0o, g1o, mode=mode), TOL, 'oracle W=%d' % W)
+        for lo, hi in ((yl, [None]), (torch.zeros_like(yl), yh)):
+            with _ffi.generic_kernels():
+                ya = i((lo, hi))
+            yb = i((lo, hi))
+            assert (ya - yb).abs().max().item() <= 1e-6 * max(1.0, ya.abs().max().item()), W
+        # FWD_J1.backward = the level-1 inverse with the analysis filters
+        x = torch.randn(1, 2, H, W, device=DEV, requires_grad=True)
+        gl, gh = torch.randn(1, 2, H, W, device=DEV), torch.randn(1, 2, 6, H // 2, W // 2, 2, device=DEV)
+        grads = []
+        for generic in (True, False):
+            x.grad = None
+            if generic:
+                with _ffi.generic_kernels():
+                    yl_, yh_ = f(x)
+                    (yl_ * gl).sum().add((yh_[0] * gh).sum()).backward()
+            else:
+                yl_, yh_ = f(x)
+                (yl_ * gl).sum().add((yh_[0] * gh).sum()).backward()
+            grads.append(x.grad.clone())
+        assert (grads[0] - grads[1]).abs().max().item() <= 1e-5 * max(1.0, grads[0].abs().max().item()), W
+
+
+@pytest.mark.parametrize('mode', ['zero', 'symmetric', 'reflect', 'periodic'])
+@pytest.mark.parametrize('wave', ['db1', 'db2', 'db3', 'db4'])
+def test_wide_synthesis_kernel_every_width_matches_generic_and_oracle(wave, mode):
+    """The wide synthesis kernel (sfb2d_stream4: 4 coefficient columns per lane, 128-column strips; taken when a plane has
+    more than 64 coefficient column pairs): every output width around the strip / vector boundaries, odd heights, cropped
+    outputs (AFB2D.backward), a missing band-pass tensor -- against the generic tile kernel (tolerance: the passes run in
+    the other order) and the oracle."""
+    torch.manual_seed(43)
+    g = pw.DWTInverse(wave=wave, mode=mode).to(DEV)
+    L = g.g0_col.numel()
+    gf = [_n(b) for b in (g.g0_col, g.g1_col, g.g0_row, g.g1_row)]
+    widths = list(range(65, 75)) + list(range(125, 135)) + [192, 193, 255, 256, 257, 259, 300]
+    for k, wc in enumerate(widths):
+        hc = 9 + (k % 5)
+        yl = torch.randn(2, 2, hc, wc, device=DEV)
+        yh = [torch.randn(2, 2, 3, hc, wc, device=DEV)]
+        with _ffi.generic_kernels():
+            ya = g((yl, yh))
+        yb = g((yl, yh))
+        assert ya.shape == yb.shape, (wc, ya.shape, yb.shape)
+        assert (ya - yb).abs().max().item() <= 1e-5 * max(1.0, ya.abs().max().item()), wc
+        if k % 6 == 0:
+            util.assert_close(_n(yb), orc.dwt_inverse(_n(yl), [_n(yh[0])], gf, mode), TOL, 'vs oracle, Wc=%d' % wc)
+    # band-pass absent (zeros), and a cropped output as AFB2D.backward requests it
+    from pytorch_wavelets_b200.dwt import lowlevel
+    m = lowlevel.mode_to_int(mode)
+    yl = torch.randn(1, 3, 20, 131, device=DEV)
+    hi = torch.randn(1, 3, 3, 20, 131, device=DEV)
+    for highs, out_hw in ((None, None), (hi, (2 * 20 - L + 1, 2 * 131 - L - 1))):
+        with _ffi.generic_kernels():
+            ya = lowlevel.sfb2d_level(yl, highs, g.g0_row, g.g1_row, g.g0_col, g.g1_col, m, out_hw=out_hw)
+        yb = lowlevel.sfb2d_level(yl, highs, g.g0_row, g.g1_row, g.g0_col, g.g1_col, m, out_hw=out_hw)
+        assert ya.shape == yb.shape
+        assert (ya - yb).abs().max().item() <= 1e-5 * max(1.0, ya.abs().max().item())
+
+
 @pytest.mark.parametrize('wave,size', [('db4', 16), ('db4', 32), ('db8', 32), ('db8', 48), ('db2', 8)])
 def test_periodization_full_depth_pyramid_down_to_1x1(wave, size):
     """planes smaller than the filter at the deep levels -- the rotation L/2-1 of the
