@@ -221,6 +221,9 @@ inline void launch_afb_kernel(const AfbParams& p, cudaStream_t stream, long long
   afb2d_stream<L, PW, MINB, HSM, XM><<<(unsigned)blocks, 32, C::SMEM_BYTES, stream>>>(p, n_strips, n_chunks, CH, k_rem, swid);
 }
 
+#ifndef B200W_AFB_SHORT_MINB
+#define B200W_AFB_SHORT_MINB 1
+#endif
 #ifndef B200W_AFB_LONG_MINB
 #define B200W_AFB_LONG_MINB 12  /* resident one-warp CTAs per SM the >= 14-tap instantiations are compiled for: 152
                                   * registers instead of 169, configs[4] chunk 1.50 -> 1.43 ms (16: spills, 1.97 ms) */
@@ -231,7 +234,7 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   const long long groups = ((long long)p.planes + G - 1) / G;
   int n_chunks, CH;
   static ConcCache conc_cache;
-  const int conc = resident_warps_dev(conc_cache, afb2d_stream<L, PW, (L >= 14 ? B200W_AFB_LONG_MINB : 1), 2, 0>,
+  const int conc = resident_warps_dev(conc_cache, afb2d_stream<L, PW, (L >= 14 ? B200W_AFB_LONG_MINB : B200W_AFB_SHORT_MINB), 2, 0>,
                                       AfbCfg<L, PW, 2, 0>::SMEM_BYTES);
   pick_chunks(groups * n_strips, p.Ho, 16, (L - 2) / 2 + 8, conc, &n_chunks, &CH);
   const long long blocks = groups * n_strips * n_chunks;
@@ -247,7 +250,7 @@ inline int launch_afb_part(const AfbParams& p, cudaStream_t stream, int n_strips
   }
   // measured and not kept: register caps (__launch_bounds__(32, 18..32): a little faster on the small levels, 15 % slower
   // on the large one) and 8-row stages (1.97 vs 1.91 ms) -- profiles/r01_notes.md
-  launch_afb_kernel<L, PW, (L >= 14 ? B200W_AFB_LONG_MINB : 1), 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
+  launch_afb_kernel<L, PW, (L >= 14 ? B200W_AFB_LONG_MINB : B200W_AFB_SHORT_MINB), 2>(p, stream, blocks, n_strips, n_chunks, CH, k_rem);
   return 0;
 }
 

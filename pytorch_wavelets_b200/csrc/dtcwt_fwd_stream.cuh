@@ -376,8 +376,11 @@ __device__ __forceinline__ void j2_dispatch(int uu, const DtParams& p, const flo
   }
 }
 
+#ifndef B200W_FWDJ2_MINB
+#define B200W_FWDJ2_MINB 1
+#endif
 template <int MQ>
-__global__ void __launch_bounds__(32) fwd_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+__global__ void __launch_bounds__(32, B200W_FWDJ2_MINB) fwd_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
                                                         int n_chunks, int CH /* quad rows per chunk */) {
   using C = J2Cfg<MQ>;
   extern __shared__ __align__(16) float ring[];

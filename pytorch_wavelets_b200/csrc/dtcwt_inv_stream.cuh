@@ -489,8 +489,11 @@ __device__ __forceinline__ void i2_dispatch(int uu, const DtParams& p, const flo
   }
 }
 
+#ifndef B200W_INVJ2_MINB
+#define B200W_INVJ2_MINB 1
+#endif
 template <int MQ>
-__global__ void __launch_bounds__(32) inv_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+__global__ void __launch_bounds__(32, B200W_INVJ2_MINB) inv_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
                                                         int n_chunks, int CH /* complex rows per chunk */) {
   using C = I2Cfg<MQ>;
   using QS = QuadStager<C::HLA, C::NS, C::MS>;

@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
 // 10 LDGSTS + 4 LDS.128 + 2 STG.128 (-38 % memory instructions, -33 % shared-memory wavefronts); the 512-wide level
 // is exactly two strips (no remainder strip).  Same arithmetic and summation order as the 2-column form.
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef B200W_SFB4_NS
+#define B200W_SFB4_NS 2   /* ring depth in stages: 2 -> 10 KB per warp, 17 warps/SM (3: 15 KB, 14 warps; inverse 2.69 -> 2.57 ms) */
+#endif
+#ifndef B200W_SFB4_MINB
+#define B200W_SFB4_MINB 1
+#endif
 template <int L>
 struct Sfb4Cfg {
   static constexpr int HALF = L / 2;
@@ -272,7 +278,7 @@ struct Sfb4Cfg {
   static constexpr int SWB = 32 * NCOPY;                           // staged floats per band row
   static constexpr int KR = (HALF % 2 == 0) ? 2 : 1;               // coefficient rows per stage
   static constexpr int UNS = HALF / KR;                            // window period in stages
-  static constexpr int NS = 3;
+  static constexpr int NS = B200W_SFB4_NS;
   static constexpr int STAGE = KR * 4 * SWB;
   static constexpr int SMEM_BYTES = NS * STAGE * 4;
   static constexpr int NW = 4 + HALF - 1;                          // window of a lane in a band row
@@ -364,7 +370,7 @@ __device__ __forceinline__ void sfb4_stage_dispatch(int vv, const SfbParams& p, 
 }
 
 template <int L>
-__global__ void __launch_bounds__(32) sfb2d_stream4(const __grid_constant__ SfbParams p, int n_strips, int n_chunks,
+__global__ void __launch_bounds__(32, B200W_SFB4_MINB) sfb2d_stream4(const __grid_constant__ SfbParams p, int n_strips, int n_chunks,
                                                     int CH /* output row pairs per chunk */) {
   using C = Sfb4Cfg<L>;
   extern __shared__ __align__(16) float ring[];
