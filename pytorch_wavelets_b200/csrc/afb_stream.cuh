@@ -155,7 +155,7 @@ __device__ __forceinline__ void afb_stage_dispatch(int vv, const AfbParams& p, c
 // strip0 / n_strips: the 64-column strips this launch covers (PW == 32), or the single remainder strip
 // starting at output column k_rem (PW < 32, n_strips == 1).
 template <int L, int PW, int MINB, int HSM, int XM>
-__global__ void __launch_bounds__(32, MINB) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
+__global__ void __launch_bounds__(32, (MINB > 1 ? MINB : 0)) afb2d_stream(const __grid_constant__ AfbParams p, int n_strips, int n_chunks,
                                                    int CH, int k_rem, int swid) {
   using C = AfbCfg<L, PW, HSM, XM>;
   extern __shared__ __align__(16) float ring[];  // this warp's staging ring

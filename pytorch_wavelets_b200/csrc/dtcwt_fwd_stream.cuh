@@ -156,8 +156,15 @@ __device__ __forceinline__ void j1_dispatch(int uu, const DtParams& p, const flo
 #ifndef B200W_J1_MINB
 #define B200W_J1_MINB 1
 #endif
+// (an explicit minBlocks of 1 is not neutral: ptxas then spends registers freely -- fwd_j2plus 156 -> 176, fwd_j1 96 -> 124 --
+// so the plain form is used unless a cap is asked for)
+#if B200W_J1_MINB > 1
+#define B200W_J1_LB __launch_bounds__(32, B200W_J1_MINB)
+#else
+#define B200W_J1_LB __launch_bounds__(32)
+#endif
 template <int L0, int L1, int SCAT>
-__global__ void __launch_bounds__(32, B200W_J1_MINB) fwd_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+__global__ void B200W_J1_LB fwd_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
                                                     int CH /* quad rows per chunk */) {
   using C = J1Cfg<L0, L1>;
   extern __shared__ __align__(16) float ring[];
@@ -379,8 +386,15 @@ __device__ __forceinline__ void j2_dispatch(int uu, const DtParams& p, const flo
 #ifndef B200W_FWDJ2_MINB
 #define B200W_FWDJ2_MINB 1
 #endif
+// (an explicit minBlocks of 1 is not neutral: ptxas then spends registers freely -- fwd_j2plus 156 -> 176, fwd_j1 96 -> 124 --
+// so the plain form is used unless a cap is asked for)
+#if B200W_FWDJ2_MINB > 1
+#define B200W_FWDJ2_LB __launch_bounds__(32, B200W_FWDJ2_MINB)
+#else
+#define B200W_FWDJ2_LB __launch_bounds__(32)
+#endif
 template <int MQ>
-__global__ void __launch_bounds__(32, B200W_FWDJ2_MINB) fwd_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+__global__ void B200W_FWDJ2_LB fwd_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
                                                         int n_chunks, int CH /* quad rows per chunk */) {
   using C = J2Cfg<MQ>;
   extern __shared__ __align__(16) float ring[];

@@ -20,6 +20,20 @@ namespace fast {
 template <int HLA, int NS, int MS>
 struct QuadStager;
 
+#ifndef B200W_INVJ1_NS
+#define B200W_INVJ1_NS 3
+#endif
+#ifndef B200W_INVJ1_MINB
+#define B200W_INVJ1_MINB 1
+#endif
+// (an explicit minBlocks of 1 is not neutral: ptxas then spends registers freely -- fwd_j2plus 156 -> 176, fwd_j1 96 -> 124 --
+// so the plain form is used unless a cap is asked for)
+#if B200W_INVJ1_MINB > 1
+#define B200W_INVJ1_LB __launch_bounds__(32, B200W_INVJ1_MINB)
+#else
+#define B200W_INVJ1_LB __launch_bounds__(32)
+#endif
+
 template <int L0, int L1>
 struct I1Cfg {
   static constexpr int M0 = L0 / 2, M1 = L1 / 2, M = (M0 > M1) ? M0 : M1;
@@ -33,7 +47,7 @@ struct I1Cfg {
   static constexpr int WR = 4 * MS + 2;              // quad rows held in the register window
   static constexpr int UNR = WR / 2;                 // window period in stages
   static constexpr int PRO = 2 * MS;
-  static constexpr int NS = 3;
+  static constexpr int NS = B200W_INVJ1_NS;
   static constexpr int SMEM_BYTES = QuadStager<HLA, NS, MS>::SMEM_FLOATS * 4;
 };
 
@@ -290,7 +304,7 @@ inline bool quad_inputs_ok(const DtParams& p) {
 }
 
 template <int L0, int L1>
-__global__ void __launch_bounds__(32) inv_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
+__global__ void B200W_INVJ1_LB inv_j1_stream(const __grid_constant__ DtParams p, int n_strips, int n_chunks,
                                                     int CH /* complex rows per chunk */) {
   using C = I1Cfg<L0, L1>;
   using QS = QuadStager<C::HLA, C::NS, C::MS>;
@@ -492,8 +506,15 @@ __device__ __forceinline__ void i2_dispatch(int uu, const DtParams& p, const flo
 #ifndef B200W_INVJ2_MINB
 #define B200W_INVJ2_MINB 1
 #endif
+// (an explicit minBlocks of 1 is not neutral: ptxas then spends registers freely -- fwd_j2plus 156 -> 176, fwd_j1 96 -> 124 --
+// so the plain form is used unless a cap is asked for)
+#if B200W_INVJ2_MINB > 1
+#define B200W_INVJ2_LB __launch_bounds__(32, B200W_INVJ2_MINB)
+#else
+#define B200W_INVJ2_LB __launch_bounds__(32)
+#endif
 template <int MQ>
-__global__ void __launch_bounds__(32, B200W_INVJ2_MINB) inv_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
+__global__ void B200W_INVJ2_LB inv_j2plus_stream(const __grid_constant__ DtParams p, int n_strips,
                                                         int n_chunks, int CH /* complex rows per chunk */) {
   using C = I2Cfg<MQ>;
   using QS = QuadStager<C::HLA, C::NS, C::MS>;

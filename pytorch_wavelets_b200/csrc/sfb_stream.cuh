@@ -270,6 +270,13 @@ __global__ void __launch_bounds__(32) sfb2d_stream(const __grid_constant__ SfbPa
 #ifndef B200W_SFB4_MINB
 #define B200W_SFB4_MINB 1
 #endif
+// (an explicit minBlocks of 1 is not neutral: ptxas then spends registers freely -- fwd_j2plus 156 -> 176, fwd_j1 96 -> 124 --
+// so the plain form is used unless a cap is asked for)
+#if B200W_SFB4_MINB > 1
+#define B200W_SFB4_LB __launch_bounds__(32, B200W_SFB4_MINB)
+#else
+#define B200W_SFB4_LB __launch_bounds__(32)
+#endif
 template <int L>
 struct Sfb4Cfg {
   static constexpr int HALF = L / 2;
@@ -370,7 +377,7 @@ __device__ __forceinline__ void sfb4_stage_dispatch(int vv, const SfbParams& p, 
 }
 
 template <int L>
-__global__ void __launch_bounds__(32, B200W_SFB4_MINB) sfb2d_stream4(const __grid_constant__ SfbParams p, int n_strips, int n_chunks,
+__global__ void B200W_SFB4_LB sfb2d_stream4(const __grid_constant__ SfbParams p, int n_strips, int n_chunks,
                                                     int CH /* output row pairs per chunk */) {
   using C = Sfb4Cfg<L>;
   extern __shared__ __align__(16) float ring[];

@@ -23,5 +23,8 @@ cap sfb4_c2 sfb2d_stream4 5 dwtinv 128 2
 cap scat_l2 fwd_j1_stream 3 scat 256 2
 cap afb16_c5 afb2d_stream 4 c5 8 2
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_prims.py tests/test_gpu_f64.py -x -q -m gpu -k "golden or periodization_full_depth or distinct_row_col or noncontiguous or wide or prims or f64 or other_families" > $O/r02b_sanitizer_memcheck.log 2>&1; echo memcheck rc=$?; tail -4 $O/r02b_sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pyramid.py -x -q -m gpu -k "dwt_golden or scat_golden or wide_synthesis or (dtcwt_golden and (J3_64 or J2_40)) or pyramid" > $O/r02b_sanitizer_racecheck.log 2>&1; echo racecheck rc=$?; tail -4 $O/r02b_sanitizer_racecheck.log
+# racecheck over the kernels that synchronise with __syncwarp / __syncthreads / cp.async groups (what the tool models).  The
+# pyramid kernel's mbarrier + TMA complete_tx ordering is not modelled (every producer -> consumer pair is flagged: excerpt
+# in profiles/r02b_sanitizer_racecheck_pyramid_excerpt.log, discussion in profiles/r02_notes.md), so its tests are left out.
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_prims.py -x -q -m gpu -k "dwt_golden or scat_golden or (wide_synthesis and db2) or (dtcwt_golden and (J3_64 or J2_40)) or (prims and qshift_a)" > $O/r02b_sanitizer_racecheck.log 2>&1; echo racecheck rc=$?; tail -4 $O/r02b_sanitizer_racecheck.log
 ls -la $O | grep r02b_ | head -40
