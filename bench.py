@@ -368,7 +368,10 @@ def run_ours(args):
     roof = None
     with torch.no_grad():
         dwt1 = pw.DWTForward(J=1, wave='db4', mode='symmetric').to(dev)
-        t1 = timed(torch, lambda: dwt1(xd), args.steps, warm=3) / 1e3
+        # five batches of >= 10 launches; the median batch average is reported (one transiently slow batch -- seen once in
+        # ~10 runs: 1.65 vs 1.55 ms with clean clocks -- must not decide the headline fraction) and all five are kept
+        t1_batches = [timed(torch, lambda: dwt1(xd), max(10, args.steps // 2), warm=3 if i == 0 else 1) / 1e3 for i in range(5)]
+        t1 = sorted(t1_batches)[2]
     alg1 = dwt_alg_bytes(dshape[0] * dshape[1], 512, 512, 8, 1)
     # secondary: the traffic of a one-pass-per-level design, i.e. the algorithmic bytes plus every inter-level
     # low-pass written once and read once (DWT: 259^2 and 133^2 per plane; DTCWT: 1024^2 and 512^2 per plane)
@@ -384,6 +387,7 @@ def run_ours(args):
     roof = {'bound': 'hbm', 'kernel': 'dwt_pyramid<8> (level 1 of DWTForward: TMA row loads, bulk stores), %dx512x512' % (dshape[0] * 32),
             'achieved': alg1 / t1 / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': alg1 / t1 / 1e9 / peak, 'traffic': traffic,
             'peak_source': peak_src, 'alg_bytes_per_launch': alg1, 'avg_launch_ms': 1e3 * t1,
+            'launch_ms_batches': [round(1e3 * t, 4) for t in t1_batches],
             'share_of_step': t1 * args.steps / (t_d + t_t),
             'whole_transform': {'dwt_fwd_GBps': parts['dwt_fwd']['GBps'], 'dwt_frac': parts['dwt_fwd']['frac'],
                                 'dtcwt_fwd_GBps': parts['dtcwt_fwd']['GBps'], 'dtcwt_frac': parts['dtcwt_fwd']['frac'],
