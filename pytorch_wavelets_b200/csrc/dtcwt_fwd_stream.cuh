@@ -30,7 +30,15 @@ __device__ __forceinline__ void q2c_emit(float a, float b, float c, float d, flo
 // call per use; twelve of them per stage serialise twelve dependent MUFU chains, which is what bounded the ScatLayer
 // kernel (profiles/r02_notes.md).  The result is the correctly rounded root except for rare 1-ulp ties -- far inside the
 // 1e-5 parity tolerance against the reference's torch.sqrt.
+// SAFE = false: the argument is known to be >= magbias^2 >= 1e-30 (the usual case, magbias = 1e-2): no rescaling, no zero test.
+template <bool SAFE>
 __device__ __forceinline__ float sqrt_nonneg(float s) {
+  if (!SAFE) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+    const float g = s * y;
+    return fmaf(fmaf(-g, g, s), 0.5f * y, g);
+  }
   const bool tiny = s < 1e-30f;
   const float t = tiny ? s * 18446744073709551616.f : s;          // x 2^64 (exact)
   float y;
@@ -45,19 +53,20 @@ __device__ __forceinline__ float sqrt_nonneg(float s) {
 
 // ScatLayer epilogue for one subband quad: smoothed magnitudes of w1 / w2 (+ re/r, im/r when DERIV: the tensors the
 // backward pass needs -- a separate instantiation, so the inference kernel carries no division code)
-template <bool DERIV>
-__device__ __forceinline__ void scat_emit(float a, float b, float c, float d, const DtParams& p, long long zbase,
+template <bool DERIV, bool SAFE>
+__device__ __forceinline__ void scat_emit(float a, float b, float c, float d, const DtParams& p, float* z1, float* z2,
                                           long long dbase, long long ostride, int o1, int o2) {
   a = __fmul_rn(a, kInvSqrt2); b = __fmul_rn(b, kInvSqrt2);
   c = __fmul_rn(c, kInvSqrt2); d = __fmul_rn(d, kInvSqrt2);
   const float re[2] = {__fsub_rn(a, d), __fadd_rn(a, d)};
   const float im[2] = {__fadd_rn(b, c), __fsub_rn(b, c)};
   const int os[2] = {o1, o2};
+  float* const zq[2] = {z1, z2};                      // this lane's element of the magnitude planes of o1, o2
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const float rr = __fmul_rn(re[k], re[k]), ii = __fmul_rn(im[k], im[k]);
-    const float r = sqrt_nonneg(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
-    __stcs(p.z + zbase + (1 + os[k]) * ostride, __fsub_rn(r, p.magbias));
+    const float r = sqrt_nonneg<SAFE>(__fadd_rn(__fadd_rn(rr, ii), p.magbias2));
+    __stcs(zq[k], __fsub_rn(r, p.magbias));
     if (DERIV) {
       __stcs(p.dre + dbase + os[k] * ostride, __fdiv_rn(re[k], r));
       __stcs(p.dim + dbase + os[k] * ostride, __fdiv_rn(im[k], r));
@@ -207,6 +216,12 @@ __global__ void B200W_J1_LB fwd_j1_stream(const __grid_constant__ DtParams p, in
   const long long zplane = ((long long)n * 7 * p.C + ch) * h2 * w2;
   const long long dplane = ((long long)n * 6 * p.C + ch) * h2 * w2;
   long long zoff = (long long)qy0 * w2 + (c0 >> 1) + lane;
+  // ScatLayer: this lane's element of the seven output planes (avg-pooled low-pass + six magnitudes), advanced by one
+  // output row per stage (pointer increments instead of seven 64-bit address computations per stage)
+  float* zp[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) zp[k] = SCAT ? p.z + zplane + zoff + k * ostride : nullptr;
+  const bool tiny_bias = !(p.magbias2 >= 1e-30f);     // magbias = 0 (or denormal): the root needs its zero / tiny handling
 
   int uu = 0;
 #pragma unroll 1
@@ -232,15 +247,26 @@ __global__ void B200W_J1_LB fwd_j1_stream(const __grid_constant__ DtParams p, in
           float s = __fadd_rn(v.vll[0][0], v.vll[0][1]);
           s = __fadd_rn(s, v.vll[1][0]);
           s = __fadd_rn(s, v.vll[1][1]);
-          __stcs(p.z + zplane + zoff, __fmul_rn(s, 0.25f));
-          scat_emit<SCAT == 2>(v.vlh[0][0], v.vlh[0][1], v.vlh[1][0], v.vlh[1][1], p, zplane + zoff, dplane + zoff, ostride, 0, 5);
-          scat_emit<SCAT == 2>(v.vhh[0][0], v.vhh[0][1], v.vhh[1][0], v.vhh[1][1], p, zplane + zoff, dplane + zoff, ostride, 1, 4);
-          scat_emit<SCAT == 2>(v.vhl[0][0], v.vhl[0][1], v.vhl[1][0], v.vhl[1][1], p, zplane + zoff, dplane + zoff, ostride, 2, 3);
+          __stcs(zp[0], __fmul_rn(s, 0.25f));
+          const long long db = dplane + zoff;
+          if (!tiny_bias) {
+            scat_emit<SCAT == 2, false>(v.vlh[0][0], v.vlh[0][1], v.vlh[1][0], v.vlh[1][1], p, zp[1], zp[6], db, ostride, 0, 5);
+            scat_emit<SCAT == 2, false>(v.vhh[0][0], v.vhh[0][1], v.vhh[1][0], v.vhh[1][1], p, zp[2], zp[5], db, ostride, 1, 4);
+            scat_emit<SCAT == 2, false>(v.vhl[0][0], v.vhl[0][1], v.vhl[1][0], v.vhl[1][1], p, zp[3], zp[4], db, ostride, 2, 3);
+          } else {
+            scat_emit<SCAT == 2, true>(v.vlh[0][0], v.vlh[0][1], v.vlh[1][0], v.vlh[1][1], p, zp[1], zp[6], db, ostride, 0, 5);
+            scat_emit<SCAT == 2, true>(v.vhh[0][0], v.vhh[0][1], v.vhh[1][0], v.vhh[1][1], p, zp[2], zp[5], db, ostride, 1, 4);
+            scat_emit<SCAT == 2, true>(v.vhl[0][0], v.vhl[0][1], v.vhl[1][0], v.vhl[1][1], p, zp[3], zp[4], db, ostride, 2, 3);
+          }
         }
       }
       ll_ptr += 2 * p.outpitch;
       hq += p.hs[3];
       zoff += (p.W >> 1);
+      if (SCAT) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) zp[k] += (p.W >> 1);
+      }
     }
   }
   cp_async_wait<0>();

@@ -279,6 +279,26 @@ def test_scat_vs_oracle(biort, shape, mode):
     util.assert_close(_n(z), oz, TOL)
 
 
+@pytest.mark.parametrize('magbias', [0.0, 1e-20, 1e-2, 3.0])
+def test_scat_magbias_range_and_zero_input(magbias):
+    """The ScatLayer epilogue has two square-root paths: the plain one when magbias^2 >= 1e-30 and one that rescales tiny
+    arguments and returns 0 for 0 (magbias = 0, where the reference computes sqrt(0) - 0 on flat regions).  Both against
+    the oracle, on an image with an all-zero plane, a constant plane and tiny values."""
+    torch.manual_seed(9)
+    x = torch.randn(2, 3, 32, 64)
+    x[0, 1] = 0.0
+    x[1, 0] = 2.5
+    x[1, 2] *= 1e-18
+    s = pw.ScatLayer(magbias=magbias)
+    oz = orc.scat_layer(x.numpy(), (s.h0o.data.numpy(), s.h1o.data.numpy()), 'symmetric', magbias)
+    z = _n(s.to(DEV)(x.to(DEV)))
+    assert np.isfinite(z).all()
+    util.assert_close(z, oz, TOL)
+    if magbias == 0.0:
+        zero_plane = z[0].reshape(7, 3, 16, 32)[1:, 1]             # magnitudes of the all-zero input plane
+        assert np.array_equal(zero_plane, np.zeros_like(zero_plane))
+
+
 # ---------------------------------------------------------------- autograd (adjoint identities)
 
 def _dot(a, b):
