@@ -31,7 +31,7 @@ struct AfbCfg {
   static constexpr int HS = (HS0 < HSM) ? HS0 : HSM;
   static constexpr int RPS = 2 * HS;                 // image rows per stage
 #ifndef B200W_AFB_NS
-#define B200W_AFB_NS 3
+#define B200W_AFB_NS 4   /* 2: -4.5 %, 3 -> 4: +0.4..0.8 % (levels 2/3 of configs[1], configs[4]) */
 #endif
   static constexpr int NS = (HS == 4) ? 2 : ((HS == 2) ? B200W_AFB_NS : 4);  // ring depth in stages
   static constexpr int NFIX = (PW == 32) ? (RPS * 2 * (HLA + L) + 31) / 32 : 8;  // border fix-ups per lane per stage

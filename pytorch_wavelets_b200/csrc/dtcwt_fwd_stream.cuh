@@ -317,6 +317,9 @@ int try_launch_scat_j1(const DtParams& p, cudaStream_t stream) {
 //   strip = 32 q = 128 input columns; stage = 4 input rows = 2 half-resolution rows = 1 quad row.
 //   taps: f0=h0a f1=h1a f2=h0b f3=h1b (stored).
 // ================================================================================================
+#ifndef B200W_FWDJ2_NS
+#define B200W_FWDJ2_NS 4   /* ring depth: 2 -> 1.207 ms, 3 -> 1.137 ms, 4 -> 1.125 ms (DTCWT forward, configs[2]) */
+#endif
 template <int MQ>
 struct J2Cfg {
   static constexpr int HL = MQ - 2;
@@ -328,7 +331,7 @@ struct J2Cfg {
   static constexpr int WR = 2 * MQ;
   static constexpr int UNR = MQ / 2;
   static constexpr int PRO = (MQ - 2) / 2;
-  static constexpr int NS = 3;
+  static constexpr int NS = B200W_FWDJ2_NS;
   static constexpr int NFIX = (4 * 2 * HLA + 31) / 32;
   static constexpr int SMEM_BYTES = (NS * 4 * SW + 2 * NS) * 4;
   using Loader = StripLoader<4, SW, NS, NFIX>;

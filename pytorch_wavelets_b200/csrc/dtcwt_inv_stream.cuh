@@ -398,6 +398,9 @@ struct IfPhase {  // dtcwt/lowlevel.py:169-186
   static constexpr int omax = (M2 % 2 == 0) ? 3 : 2;
 };
 
+#ifndef B200W_INVJ2_NS
+#define B200W_INVJ2_NS 3
+#endif
 template <int MQ>
 struct I2Cfg {
   static constexpr int M2 = MQ / 2;
@@ -414,7 +417,7 @@ struct I2Cfg {
   static constexpr int WR = 4 * MS + 2;
   static constexpr int UNR = WR / 2;
   static constexpr int PRO = 2 * MS;
-  static constexpr int NS = 3;
+  static constexpr int NS = B200W_INVJ2_NS;
   static constexpr int SMEM_BYTES = QuadStager<HLA, NS, MS>::SMEM_FLOATS * 4;
 };
 

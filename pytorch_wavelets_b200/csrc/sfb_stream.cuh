@@ -282,7 +282,7 @@ struct Sfb4Cfg {
   static constexpr int HALF = L / 2;
   static constexpr int CW = 128;                                   // coefficient columns per strip (4 per lane)
   static constexpr int NCOPY = (CW + HALF - 1 + 31) / 32;          // 32-lane copies per staged band row
-  static constexpr int SWB = 32 * NCOPY;                           // staged floats per band row
+  static constexpr int SWB = (CW + HALF - 1 + 3) / 4 * 4;         // staged floats per band row (16-byte multiple)
   static constexpr int KR = (HALF % 2 == 0) ? 2 : 1;               // coefficient rows per stage
   static constexpr int UNS = HALF / KR;                            // window period in stages
   static constexpr int NS = B200W_SFB4_NS;
