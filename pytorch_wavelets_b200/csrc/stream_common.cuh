@@ -362,6 +362,17 @@ inline void pick_chunks(long long base_items, int rows_out, int min_rows, int pr
     const double cost = work + 0.5 * (ch + pro);
     if (nc == 1 || cost < best) { best = cost; best_ch = ch; best_nc = n; }
   }
+#ifdef B200W_CHUNK_SCALE_NUM   /* experiments: scale the chosen chunk count (variant builds only) */
+  {
+    int nc = best_nc * B200W_CHUNK_SCALE_NUM / B200W_CHUNK_SCALE_DEN;
+    if (nc < 1) nc = 1;
+    if (nc > max_chunks) nc = max_chunks;
+    int ch = (rows_out + nc - 1) / nc;
+    ch = (ch + min_rows - 1) / min_rows * min_rows;
+    best_ch = ch;
+    best_nc = (rows_out + ch - 1) / ch;
+  }
+#endif
   *CH = best_ch;
   *n_chunks = best_nc;
 }
