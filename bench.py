@@ -366,6 +366,11 @@ def run_ours(args):
 
     # -- roofline of the dominant kernel: the level-1 pyramid kernel, timed alone as DWTForward(J=1) (= one launch)
     roof = None
+    # The J = 1 launch writes 4.4 GB of freshly allocated outputs per call; its time depends on where those land (1.55 ms in
+    # most processes / batches, up to 1.64 ms in others, with the J = 3 step time unchanged: profiles/r02_notes.md).  The cache is
+    # emptied first so that the placement is the first-call one, and the median of five batches is reported with all five.
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     with torch.no_grad():
         dwt1 = pw.DWTForward(J=1, wave='db4', mode='symmetric').to(dev)
         # five batches of >= 10 launches; the median batch average is reported (one transiently slow batch -- seen once in
