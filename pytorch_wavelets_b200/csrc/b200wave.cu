@@ -271,9 +271,9 @@ static void dwt_ws_layout(int planes, int H, int W, int J, int Lw, int Lh, int m
 //   kLevels       one K1 launch per level
 // Measured on B200 (profiles/r02_notes.md, tools/policy_probe.py; 268 Mpix per call, J = 3, db4): with more than one
 // level in the kernel an 8-warp CTA (planes narrower than ~700 columns) is register / shared-memory bound to 2 per SM,
-// which costs more than the hand-off traffic it saves (512^2: 0.73 vs 0.68 ms, 256^2: 1.34 vs 0.87 ms), while the
-// single-level form runs 3 CTAs per SM and beats the streaming kernel (1.67 vs 1.97 ms); from 1024 columns up a CTA
-// has enough level-1 warps and the single launch wins (1024^2: 0.71 vs 0.77 ms).
+// which costs more than the hand-off traffic it saves (512^2: 0.73 vs 0.64 ms, 256^2: 1.34 vs 0.89 ms), while the
+// single-level form runs 4 CTAs per SM and beats the streaming kernel (1.55 vs 1.97 ms); from 1024 columns up a CTA
+// has enough level-1 warps and the single launch wins (1024^2: 0.70 vs 0.77 ms).
 enum DwtPolicy { kLevels = 0, kPyramidFirst = 1, kPyramidAll = 2 };
 
 #ifndef B200W_PYR_FUSE_ALL_MIN_WIDTH
