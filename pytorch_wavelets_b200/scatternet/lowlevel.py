@@ -61,13 +61,20 @@ class ScatLayerj1_f(Function):
             drdx, drdy = ctx.saved_tensors
             dYl, dr = dZ[:, 0], dZ[:, 1:]
             ll = 1 / 4 * F.interpolate(dYl, scale_factor=2, mode='nearest')
-            # band-pass gradient as one tensor with real/imag outermost: dims (r, n, o, c, h, w)
-            highs = torch.stack((dr * drdx, dr * drdy), dim=0)
-            dX = _inv_j1_ri_first(ll, highs, h0o, h1o, ctx.mode)
+            # band-pass gradient written straight into the (n, o, c, h, w, re/im) layout: re/im adjacent and columns
+            # contiguous is all the streaming level-1 synthesis kernel needs (the orientation / channel order travels as
+            # strides), so the backward runs on the fast path (round 1: (r, n, o, c, h, w) -> the 4x slower generic kernel)
+            if dr.requires_grad:      # (create_graph=True: `out=` is not differentiable)
+                highs = torch.stack((dr * drdx, dr * drdy), dim=-1)
+            else:
+                highs = dr.new_empty(dr.shape + (2,))
+                torch.mul(dr, drdx, out=highs[..., 0])
+                torch.mul(dr, drdy, out=highs[..., 1])
+            dX = _inv_j1_o1_ri_last(ll, highs, h0o, h1o, ctx.mode)
         return (dX,) + (None,) * 5
 
 
-def _inv_j1_ri_first(ll, highs, g0, g1, mode):
-    """inv_j1 for a band-pass tensor laid out (2, N, 6, C, h, w).  transform_funcs._layout(o5, ri) inserts
-    'o' into (n,c,h,w) at o5 then 'r' at ri: o5=1 -> (n,o,c,h,w); ri=0 -> (r,n,o,c,h,w)."""
-    return inv_j1(ll, highs, g0, g1, 1, 0, mode)
+def _inv_j1_o1_ri_last(ll, highs, g0, g1, mode):
+    """inv_j1 for a band-pass tensor laid out (N, 6, C, h, w, 2).  transform_funcs._layout(o5, ri) inserts 'o' into
+    (n,c,h,w) at o5 then 'r' at ri: o5=1 -> (n,o,c,h,w); ri=5 -> (n,o,c,h,w,r)."""
+    return inv_j1(ll, highs, g0, g1, 1, 5, mode)
