@@ -76,7 +76,11 @@ def _pair(ha, hb):
     for h in (ha, hb):
         if isinstance(h, torch.Tensor) and h.dim() == 4:
             h = h[0]
-        out.append(h)
+        out.append(_ffi.host_taps(h))
+    if out[0].n != out[1].n:       # (the reference's conv2d would fail on the concatenated filter bank as well)
+        raise ValueError('ha and hb must have the same length, got {} and {}'.format(out[0].n, out[1].n))
+    if out[0].n % 2:
+        raise ValueError('q-shift filters must have an even length, got {}'.format(out[0].n))
     return out
 
 

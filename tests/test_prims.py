@@ -76,6 +76,8 @@ def test_gpu_primitives_f64_errors_and_q2c_roundtrip():
         ll.rowifilt(torch.randn(1, 1, 16, 15, device='cuda'), _t(G['qshift_a_ha']), _t(G['qshift_a_hb']))
     with pytest.raises(NotImplementedError):
         ll.rowdfilt(torch.randn(1, 1, 16, 16, device='cuda'), _t(G['qshift_a_ha']), _t(G['qshift_a_hb']), mode='zero')
+    with pytest.raises(ValueError):     # filter pair of unequal length
+        ll.coldfilt(torch.randn(1, 1, 16, 16, device='cuda'), _t(G['qshift_a_ha']), _t(G['qshift_b_hb']))
     q = torch.randn(1, 2, 8, 12, device='cuda')
     w1, w2 = ll.q2c(q)
     assert float((ll.c2q(w1, w2) - q).abs().max()) < 1e-6
