@@ -68,3 +68,46 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_ffi, 'SO_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_ffi.B200WaveError):
         _ffi.lib()
+
+
+def test_f64_and_primitive_entries_validate_without_gpu(lib):
+    """The float64 and standalone-primitive entry points share the validation of the float32 ones (csrc/k_f64.cu compiles
+    launch_params.h for double; csrc/k_prims.cu checks sizes before launching)."""
+    d = (ctypes.c_double * 10)(*([0.25] * 10))
+    dp = ctypes.cast(d, ctypes.c_void_p)
+    buf = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert lib.b200w_dwt_afb2d_f64(buf, 64, 8, buf, 49, 7, buf, 1, 8, 8, dp, dp, 8, dp, dp, 8, 99, None) == -1   # bad mode
+    assert lib.b200w_dwt_afb2d_f64(None, 64, 8, buf, 49, 7, buf, 1, 8, 8, dp, dp, 8, dp, dp, 8, 1, None) == -3  # null input
+    hs = (ctypes.c_longlong * 6)(1, 1, 1, 1, 1, 1)
+    assert lib.b200w_dtcwt_fwd_j2plus_f64(buf, 36, 6, buf, 9, 3, buf, hs, 1, 1, 6, 6, dp, dp, dp, dp, 8, None) == -2
+    f = (ctypes.c_float * 10)(*([0.25] * 10))
+    fp = ctypes.cast(f, ctypes.c_void_p)
+    # coldfilt needs rows % 4 == 0, colifilt rows % 2 == 0 (reference ValueError), q-shift filters an even length
+    assert lib.b200w_dtcwt_dfilt(buf, buf, 1, 18, 16, fp, fp, 10, 0, 0, None) == -2
+    assert lib.b200w_dtcwt_dfilt(buf, buf, 1, 16, 18, fp, fp, 10, 0, 1, None) == -2
+    assert lib.b200w_dtcwt_ifilt(buf, buf, 1, 15, 16, fp, fp, 10, 0, 0, None) == -2
+    assert lib.b200w_dtcwt_dfilt(buf, buf, 1, 16, 16, fp, fp, 9, 0, 0, None) == -4
+    assert lib.b200w_dtcwt_filter(None, buf, 1, 16, 16, fp, 4, 1, 0, None) == -3
+    assert lib.b200w_dtcwt_filter(buf, buf, 1, 16, 16, fp, 41, 1, 0, None) == -4       # longer than B200W_MAX_TAPS
+    # empty batches are a no-op everywhere (no launch, no CUDA call)
+    assert lib.b200w_dtcwt_filter(buf, buf, 0, 16, 16, fp, 4, 1, 0, None) == 0
+    assert lib.b200w_dtcwt_filter_f64(buf, buf, 0, 16, 16, dp, 5, 0, 1, None) == 0
+
+
+def test_shells_refuse_cpu_tensors_and_unsupported_dtypes():
+    """No CPU or eager fallback anywhere: CPU tensors and dtypes other than float32 / float64 raise."""
+    import torch
+    import pytorch_wavelets_b200 as pw
+    from pytorch_wavelets_b200.dtcwt import lowlevel as ll
+    x = torch.randn(1, 1, 16, 16)
+    for mod in (pw.DWTForward(J=1, wave='bior2.2'), pw.DTCWTForward(J=1), pw.ScatLayer()):
+        with pytest.raises(NotImplementedError):
+            mod(x)
+        with pytest.raises(NotImplementedError):
+            mod.double()(x.double())
+    with pytest.raises(NotImplementedError):
+        ll.colfilter(x, torch.ones(4))
+    with pytest.raises(NotImplementedError):
+        ll.coldfilt(x, torch.ones(10), torch.ones(10))
+    with pytest.raises(NotImplementedError):
+        _ffi.require_cuda_real(torch.zeros(2, dtype=torch.float16), 'x')
